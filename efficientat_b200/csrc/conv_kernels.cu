@@ -1,0 +1,501 @@
+// Bandwidth-bound kernels of the MobileNetV3 path, NHWC activations ([B, F, T, C], C innermost):
+//   stem 3x3 conv (Cin = 1), depthwise k x k conv, BatchNorm helpers, squeeze-excitation MLP.
+// Every kernel takes an optional per-channel affine+activation on its INPUT (the BatchNorm +
+// activation of the producing layer, applied on load so the normalised tensor is never written)
+// and either a folded affine+activation epilogue (eval) or raw output + per-channel batch
+// statistics (training).  Reference semantics: torchvision ConvNormActivation as used at
+// models/mn/model.py:125-133 and models/mn/block_types.py:140-170; SqueezeExcitation
+// models/mn/block_types.py:72-83.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// ------------------------------------------------------------------------------------------
+// Block-level reduction of per-thread channel partial sums.
+// Thread layout: cvi = tid % cv (channel vector), slot = tid / cv.  s_acc has C floats (x2 if sq).
+template <int V>
+__device__ __forceinline__ void block_channel_reduce(float (&sum)[V], float* s_acc, int C, int cvi, bool active) {
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) atomicAdd(&s_acc[cvi * V + i], sum[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Stem: x [B, F, T] fp32 (one input channel) -> out [B, Fo, To, C] ; 3x3, pad 1, stride s.
+template <typename TO>
+__global__ void __launch_bounds__(kThreads) stem_kernel(
+    const float* __restrict__ x, const float* __restrict__ w /*[C,1,3,3]*/, TO* __restrict__ out,
+    int B, int F, int T, int Fo, int To, int C, int stride,
+    const float* __restrict__ scale, const float* __restrict__ shift, int act,
+    double* __restrict__ stat_sum, double* __restrict__ stat_sq) {
+  constexpr int V = Vec<TO>::N;
+  extern __shared__ float smem[];
+  float* s_w = smem;            // [9][C]
+  float* s_sum = s_w + 9 * C;   // [C]
+  float* s_sq = s_sum + C;      // [C]
+  for (int i = threadIdx.x; i < 9 * C; i += kThreads) { int c = i % C, tap = i / C; s_w[i] = w[c * 9 + tap]; }
+  for (int i = threadIdx.x; i < 2 * C; i += kThreads) s_sum[i] = 0.f;
+  __syncthreads();
+  const int cv = C / V;
+  const int ppb = kThreads / cv;
+  const int cvi = threadIdx.x % cv, slot = threadIdx.x / cv;
+  const bool active = slot < ppb;
+  const long long npix = (long long)B * Fo * To;
+  float lsum[V], lsq[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { lsum[i] = 0.f; lsq[i] = 0.f; }
+  if (active) {
+    for (long long pix = (long long)blockIdx.x * ppb + slot; pix < npix; pix += (long long)gridDim.x * ppb) {
+      int to = (int)(pix % To);
+      int fo = (int)((pix / To) % Fo);
+      int b = (int)(pix / ((long long)To * Fo));
+      float acc[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        int f = fo * stride - 1 + ky;
+        if (f < 0 || f >= F) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          int t = to * stride - 1 + kx;
+          if (t < 0 || t >= T) continue;
+          float xv = __ldg(x + ((size_t)b * F + f) * T + t);
+          const float* wp = s_w + (ky * 3 + kx) * C + cvi * V;
+#pragma unroll
+          for (int i = 0; i < V; ++i) acc[i] = fmaf(xv, wp[i], acc[i]);
+        }
+      }
+      if (scale != nullptr) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] = act_fwd(fmaf(acc[i], scale[cvi * V + i], shift[cvi * V + i]), act);
+      } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) { lsum[i] += acc[i]; lsq[i] = fmaf(acc[i], acc[i], lsq[i]); }
+      }
+      Vec<TO>::store(out + (size_t)pix * C + cvi * V, acc);
+    }
+  }
+  if (stat_sum != nullptr) {
+    block_channel_reduce<V>(lsum, s_sum, C, cvi, active);
+    block_channel_reduce<V>(lsq, s_sq, C, cvi, active);
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+      atomicAdd(stat_sum + c, (double)s_sum[c]);
+      atomicAdd(stat_sq + c, (double)s_sq[c]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Depthwise k x k conv, pad (k-1)/2, stride S.  in [B, F, T, C] -> out [B, Fo, To, C].
+// wt: repacked weights [k*k][C].  Each thread: one channel vector, a strip of P output columns.
+// grid = (chunks, B) so per-(sample, channel) pooling stays inside a CTA column.
+template <typename T, int K, int S>
+__global__ void __launch_bounds__(kThreads) dw_kernel(
+    const T* __restrict__ in, const float* __restrict__ wt, T* __restrict__ out,
+    int F, int Tn, int Fo, int To, int C, InXform xf,
+    const float* __restrict__ scale, const float* __restrict__ shift, int act,
+    float* __restrict__ pool /*[B,C] or null*/, double* __restrict__ stat_sum, double* __restrict__ stat_sq) {
+  constexpr int V = Vec<T>::N;
+  constexpr int P = 4;
+  constexpr int NIN = (P - 1) * S + K;
+  constexpr int PAD = (K - 1) / 2;
+  extern __shared__ float smem[];
+  float* s_sum = smem;       // [C]
+  float* s_sq = smem + C;    // [C]
+  const bool need_red = (pool != nullptr) || (stat_sum != nullptr);
+  if (need_red) {
+    for (int i = threadIdx.x; i < 2 * C; i += kThreads) s_sum[i] = 0.f;
+    __syncthreads();
+  }
+  const int cv = C / V;
+  const int ppb = kThreads / cv > 0 ? kThreads / cv : 1;
+  const int b = blockIdx.y;
+  const int strips = ceil_div(To, P);
+  const int units = Fo * strips;
+  float lsum[V], lsq[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { lsum[i] = 0.f; lsq[i] = 0.f; }
+  const T* inb = in + (size_t)b * F * Tn * C;
+  T* outb = out + (size_t)b * Fo * To * C;
+  // channel vectors beyond kThreads are covered by looping cvi
+  for (int cvi = threadIdx.x % (cv < kThreads ? cv : kThreads); cvi < cv; cvi += kThreads) {
+    const int slot = cv < kThreads ? threadIdx.x / cv : 0;
+    if (slot >= ppb) break;
+    const int c0 = cvi * V;
+    float isc[V], ish[V];
+    if (xf.scale != nullptr) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) { isc[i] = xf.scale[c0 + i]; ish[i] = xf.shift[c0 + i]; }
+    }
+    float osc[V], osh[V];
+    if (scale != nullptr) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) { osc[i] = scale[c0 + i]; osh[i] = shift[c0 + i]; }
+    }
+    for (int u = blockIdx.x * ppb + slot; u < units; u += gridDim.x * ppb) {
+      const int fo = u / strips;
+      const int to0 = (u - fo * strips) * P;
+      float acc[P][V];
+#pragma unroll
+      for (int p = 0; p < P; ++p)
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[p][i] = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < K; ++ky) {
+        const int f = fo * S - PAD + ky;
+        if (f < 0 || f >= F) continue;
+        const T* rowp = inb + (size_t)f * Tn * C + c0;
+        float wreg[K][V];
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          float4 const* wp = reinterpret_cast<float4 const*>(wt + (size_t)(ky * K + kx) * C + c0);
+#pragma unroll
+          for (int q = 0; q < V / 4; ++q) {
+            float4 t4 = __ldg(wp + q);
+            wreg[kx][4 * q] = t4.x; wreg[kx][4 * q + 1] = t4.y; wreg[kx][4 * q + 2] = t4.z; wreg[kx][4 * q + 3] = t4.w;
+          }
+        }
+#pragma unroll
+        for (int ix = 0; ix < NIN; ++ix) {
+          const int t = to0 * S - PAD + ix;
+          if (t < 0 || t >= Tn) continue;
+          float v[V];
+          Vec<T>::load(rowp + (size_t)t * C, v);
+          if (xf.scale != nullptr) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) v[i] = act_fwd(fmaf(v[i], isc[i], ish[i]), xf.act);
+          }
+#pragma unroll
+          for (int p = 0; p < P; ++p) {
+            const int kx = ix - p * S;
+            if (kx >= 0 && kx < K) {
+#pragma unroll
+              for (int i = 0; i < V; ++i) acc[p][i] = fmaf(v[i], wreg[kx][i], acc[p][i]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        const int to = to0 + p;
+        if (to >= To) break;
+        float o[V];
+        if (scale != nullptr) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) { o[i] = act_fwd(fmaf(acc[p][i], osc[i], osh[i]), act); lsum[i] += o[i]; }
+        } else {
+#pragma unroll
+          for (int i = 0; i < V; ++i) { o[i] = acc[p][i]; lsum[i] += o[i]; lsq[i] = fmaf(o[i], o[i], lsq[i]); }
+        }
+        Vec<T>::store(outb + ((size_t)fo * To + to) * C + c0, o);
+      }
+    }
+    if (need_red) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) { atomicAdd(&s_sum[c0 + i], lsum[i]); lsum[i] = 0.f; }
+      if (stat_sum != nullptr) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) { atomicAdd(&s_sq[c0 + i], lsq[i]); lsq[i] = 0.f; }
+      }
+    }
+  }
+  if (need_red) {
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+      if (pool != nullptr) atomicAdd(pool + (size_t)b * C + c, s_sum[c]);
+      if (stat_sum != nullptr) { atomicAdd(stat_sum + c, (double)s_sum[c]); atomicAdd(stat_sq + c, (double)s_sq[c]); }
+    }
+  }
+}
+
+// [C,1,k,k] -> [k*k][C]
+__global__ void dw_repack_kernel(const float* __restrict__ w, float* __restrict__ wt, int C, int kk) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C * kk) { int c = i / kk, tap = i % kk; wt[(size_t)tap * C + c] = w[i]; }
+}
+
+// ------------------------------------------------------------------------------------------
+// BatchNorm helpers
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ rmean, const float* __restrict__ rvar, float eps,
+                               float* __restrict__ scale, float* __restrict__ shift, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    float s = gamma[c] / sqrtf(rvar[c] + eps);
+    scale[c] = s;
+    shift[c] = beta[c] - rmean[c] * s;
+  }
+}
+
+// training: batch statistics -> scale/shift (+ saved mean / invstd), running-stat update
+// (nn.BatchNorm2d: running = (1-m) running + m batch, unbiased variance for the running buffer)
+__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sq, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* __restrict__ rmean, float* __restrict__ rvar,
+                                   long long* __restrict__ nbt, float* __restrict__ scale,
+                                   float* __restrict__ shift, float* __restrict__ save_mean,
+                                   float* __restrict__ save_invstd, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    double mean = sum[c] / count;
+    double var = sq[c] / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    float s = gamma[c] * invstd;
+    scale[c] = s;
+    shift[c] = beta[c] - (float)mean * s;
+    save_mean[c] = (float)mean;
+    save_invstd[c] = invstd;
+    if (rmean != nullptr) {
+      double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)mean;
+      rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unbiased;
+    }
+  }
+  if (nbt != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *nbt += 1;
+}
+
+// y = act(z * scale + shift) (+ residual);  elementwise over [rows, C]
+template <typename T>
+__global__ void __launch_bounds__(kThreads) bn_apply_kernel(const T* __restrict__ z, const float* __restrict__ scale,
+                                                            const float* __restrict__ shift, int act,
+                                                            const T* __restrict__ res, T* __restrict__ y,
+                                                            long long rows, int C) {
+  constexpr int V = Vec<T>::N;
+  const int cv = C / V;
+  const long long nvec = rows * cv;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += (long long)gridDim.x * kThreads) {
+    const int c0 = (int)(i % cv) * V;
+    float v[V];
+    Vec<T>::load(z + i * V, v);
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] = act_fwd(fmaf(v[k], scale[c0 + k], shift[c0 + k]), act);
+    if (res != nullptr) {
+      float r[V];
+      Vec<T>::load(res + i * V, r);
+#pragma unroll
+      for (int k = 0; k < V; ++k) v[k] += r[k];
+    }
+    Vec<T>::store(y + i * V, v);
+  }
+}
+
+// pool[b, c] += sum_p act(z[b, p, c] * scale[c] + shift[c]);  grid = (chunks, B)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) bn_act_pool_kernel(const T* __restrict__ z, const float* __restrict__ scale,
+                                                               const float* __restrict__ shift, int act,
+                                                               float* __restrict__ pool, float mul, int P, int C) {
+  constexpr int V = Vec<T>::N;
+  extern __shared__ float smem[];
+  for (int i = threadIdx.x; i < C; i += kThreads) smem[i] = 0.f;
+  __syncthreads();
+  const int cv = C / V;
+  const int b = blockIdx.y;
+  const T* zb = z + (size_t)b * P * C;
+  const long long nvec = (long long)P * cv;
+  // each thread keeps a fixed channel vector when kThreads % cv == 0 is not guaranteed, so use smem atomics per item
+  // but first accumulate privately over a stride that preserves the channel vector: stride = lcm-free trick:
+  // iterate pixels for (slot, cvi) pairs as in the conv kernels.
+  const int tcv = cv < kThreads ? cv : kThreads;
+  const int ppb = kThreads / tcv;
+  const int slot = threadIdx.x / tcv;
+  if (slot < ppb) {
+    for (int cvi = threadIdx.x % tcv; cvi < cv; cvi += tcv) {
+      const int c0 = cvi * V;
+      float acc[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] = 0.f;
+      for (int p = blockIdx.x * ppb + slot; p < P; p += gridDim.x * ppb) {
+        float v[V];
+        Vec<T>::load(zb + (size_t)p * C + c0, v);
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+          acc[k] += scale != nullptr ? act_fwd(fmaf(v[k], scale[c0 + k], shift[c0 + k]), act) : v[k];
+      }
+#pragma unroll
+      for (int k = 0; k < V; ++k) atomicAdd(&smem[c0 + k], acc[k]);
+    }
+  }
+  (void)nvec;
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kThreads) atomicAdd(pool + (size_t)b * C + c, smem[c] * mul);
+}
+
+// ------------------------------------------------------------------------------------------
+// Squeeze-excitation MLP: gate[b,:] = sigmoid(W2 relu(W1 (pool[b,:] * inv_count) + b1) + b2)
+// one CTA per sample; warp per output row (coalesced weight rows).
+__global__ void __launch_bounds__(kThreads) se_fc_kernel(const float* __restrict__ pool, float inv_count,
+                                                         const float* __restrict__ w1, const float* __restrict__ b1,
+                                                         const float* __restrict__ w2, const float* __restrict__ b2,
+                                                         float* __restrict__ gate, float* __restrict__ hidden_out,
+                                                         int C, int S) {
+  extern __shared__ float smem[];
+  float* s_mean = smem;       // [C]
+  float* s_hid = smem + C;    // [S]
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += kThreads) s_mean[c] = pool[(size_t)b * C + c] * inv_count;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = kThreads / 32;
+  for (int s = warp; s < S; s += nwarps) {
+    const float* wr = w1 + (size_t)s * C;
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc = fmaf(__ldg(wr + c), s_mean[c], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float h = fmaxf(acc + b1[s], 0.f);
+      s_hid[s] = h;
+      if (hidden_out != nullptr) hidden_out[(size_t)b * S + s] = h;
+    }
+  }
+  __syncthreads();
+  for (int c = warp; c < C; c += nwarps) {
+    const float* wr = w2 + (size_t)c * S;
+    float acc = 0.f;
+    for (int s = lane; s < S; s += 32) acc = fmaf(__ldg(wr + s), s_hid[s], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) gate[(size_t)b * C + c] = sigmoidf_(acc + b2[c]);
+  }
+}
+
+inline int grid_for(long long items, int per_block, int max_blocks = 148 * 16) {
+  long long g = ceil_div_ll(items, per_block);
+  if (g > max_blocks) g = max_blocks;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+template <typename T>
+int launch_dw(const T* in, const float* wt, T* out, int B, int F, int Tn, int C, int k, int stride, InXform xf,
+              const float* scale, const float* shift, int act, float* pool, double* ssum, double* ssq,
+              cudaStream_t st) {
+  constexpr int V = Vec<T>::N;
+  if (C % V != 0) { eat_set_error("dw conv: channels must be a multiple of the vector width"); return EAT_ERR_ARG; }
+  const int pad = (k - 1) / 2;
+  const int Fo = (F + 2 * pad - k) / stride + 1, To = (Tn + 2 * pad - k) / stride + 1;
+  const int cv = C / V;
+  const int ppb = kThreads / cv > 0 ? kThreads / cv : 1;
+  const int units = Fo * ceil_div(To, 4);
+  int gx = ceil_div(units, ppb);
+  const int cap = max(1, (148 * 8) / max(B, 1));
+  if (gx > cap) gx = cap;   // grid-stride over strips; keeps per-CTA reductions coarse
+  dim3 grid(gx, B);
+  size_t smem = 2 * (size_t)C * sizeof(float);
+#define EAT_DW(KK, SS) dw_kernel<T, KK, SS><<<grid, kThreads, smem, st>>>(in, wt, out, F, Tn, Fo, To, C, xf, scale, shift, act, pool, ssum, ssq)
+  if (k == 3 && stride == 1) EAT_DW(3, 1);
+  else if (k == 3 && stride == 2) EAT_DW(3, 2);
+  else if (k == 5 && stride == 1) EAT_DW(5, 1);
+  else if (k == 5 && stride == 2) EAT_DW(5, 2);
+  else { eat_set_error("dw conv: only k in {3,5}, stride in {1,2}"); return EAT_ERR_UNSUPPORTED; }
+#undef EAT_DW
+  EAT_CHECK_LAUNCH();
+  return EAT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int eat_stem_fwd(const float* x, const float* w, void* out, int out_dtype, int B, int F, int T, int C, int stride,
+                 const float* scale, const float* shift, int act, double* stat_sum, double* stat_sq,
+                 cudaStream_t st) {
+  const int Fo = (F + 2 - 3) / stride + 1, To = (T + 2 - 3) / stride + 1;
+  const int V = out_dtype == EAT_BF16 ? 8 : 4;
+  if (C % V != 0 || C / V > kThreads) { eat_set_error("stem: unsupported channel count"); return EAT_ERR_ARG; }
+  const long long npix = (long long)B * Fo * To;
+  if (npix == 0) return EAT_OK;
+  const int ppb = kThreads / (C / V);
+  int grid = grid_for(npix, ppb, 148 * 8);
+  size_t smem = (size_t)11 * C * sizeof(float);
+  if (out_dtype == EAT_BF16)
+    stem_kernel<__nv_bfloat16><<<grid, kThreads, smem, st>>>(x, w, (__nv_bfloat16*)out, B, F, T, Fo, To, C, stride, scale, shift, act, stat_sum, stat_sq);
+  else
+    stem_kernel<float><<<grid, kThreads, smem, st>>>(x, w, (float*)out, B, F, T, Fo, To, C, stride, scale, shift, act, stat_sum, stat_sq);
+  EAT_CHECK_LAUNCH();
+  return EAT_OK;
+}
+
+int eat_dw_repack(const float* w, float* wt, int C, int k, cudaStream_t st) {
+  int n = C * k * k;
+  dw_repack_kernel<<<ceil_div(n, 256), 256, 0, st>>>(w, wt, C, k * k);
+  EAT_CHECK_LAUNCH();
+  return EAT_OK;
+}
+
+int eat_dw_conv_fwd(const void* in, const float* wt, void* out, int dtype, int B, int F, int T, int C, int k,
+                    int stride, const float* in_scale, const float* in_shift, int in_act, const float* scale,
+                    const float* shift, int act, float* pool, double* stat_sum, double* stat_sq,
+                    cudaStream_t st) {
+  if (B == 0) return EAT_OK;
+  InXform xf{in_scale, in_shift, nullptr, in_act, 0};
+  if (dtype == EAT_BF16)
+    return launch_dw<__nv_bfloat16>((const __nv_bfloat16*)in, wt, (__nv_bfloat16*)out, B, F, T, C, k, stride, xf, scale, shift, act, pool, stat_sum, stat_sq, st);
+  return launch_dw<float>((const float*)in, wt, (float*)out, B, F, T, C, k, stride, xf, scale, shift, act, pool, stat_sum, stat_sq, st);
+}
+
+int eat_bn_fold(const float* gamma, const float* beta, const float* rmean, const float* rvar, float eps,
+                float* scale, float* shift, int C, cudaStream_t st) {
+  bn_fold_kernel<<<ceil_div(C, 128), 128, 0, st>>>(gamma, beta, rmean, rvar, eps, scale, shift, C);
+  EAT_CHECK_LAUNCH();
+  return EAT_OK;
+}
+
+int eat_bn_finalize(const double* sum, const double* sq, double count, const float* gamma, const float* beta,
+                    float eps, float momentum, float* rmean, float* rvar, long long* nbt, float* scale,
+                    float* shift, float* save_mean, float* save_invstd, int C, cudaStream_t st) {
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sum, sq, count, gamma, beta, eps, momentum, rmean, rvar, nbt,
+                                                        scale, shift, save_mean, save_invstd, C);
+  EAT_CHECK_LAUNCH();
+  return EAT_OK;
+}
+
+int eat_bn_apply(const void* z, const float* scale, const float* shift, int act, const void* res, void* y,
+                 int dtype, long long rows, int C, cudaStream_t st) {
+  if (rows == 0) return EAT_OK;
+  const int V = dtype == EAT_BF16 ? 8 : 4;
+  if (C % V != 0) { eat_set_error("bn_apply: channels must be a multiple of the vector width"); return EAT_ERR_ARG; }
+  int grid = grid_for(rows * (C / V), kThreads * 4);
+  if (dtype == EAT_BF16)
+    bn_apply_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)z, scale, shift, act, (const __nv_bfloat16*)res, (__nv_bfloat16*)y, rows, C);
+  else
+    bn_apply_kernel<float><<<grid, kThreads, 0, st>>>((const float*)z, scale, shift, act, (const float*)res, (float*)y, rows, C);
+  EAT_CHECK_LAUNCH();
+  return EAT_OK;
+}
+
+int eat_bn_act_pool(const void* z, const float* scale, const float* shift, int act, float* pool, float mul,
+                    int dtype, int B, int P, int C, cudaStream_t st) {
+  if (B == 0) return EAT_OK;
+  const int V = dtype == EAT_BF16 ? 8 : 4;
+  if (C % V != 0) { eat_set_error("bn_act_pool: channels must be a multiple of the vector width"); return EAT_ERR_ARG; }
+  const int cv = C / V;
+  const int tcv = cv < kThreads ? cv : kThreads;
+  const int ppb = kThreads / tcv;
+  int gx = ceil_div(P, ppb * 8);
+  const int cap = max(1, (148 * 8) / B);
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, B);
+  size_t smem = (size_t)C * sizeof(float);
+  if (dtype == EAT_BF16)
+    bn_act_pool_kernel<__nv_bfloat16><<<grid, kThreads, smem, st>>>((const __nv_bfloat16*)z, scale, shift, act, pool, mul, P, C);
+  else
+    bn_act_pool_kernel<float><<<grid, kThreads, smem, st>>>((const float*)z, scale, shift, act, pool, mul, P, C);
+  EAT_CHECK_LAUNCH();
+  return EAT_OK;
+}
+
+int eat_se_fc_fwd(const float* pool, float inv_count, const float* w1, const float* b1, const float* w2,
+                  const float* b2, float* gate, float* hidden_out, int B, int C, int S, cudaStream_t st) {
+  if (B == 0) return EAT_OK;
+  size_t smem = (size_t)(C + S) * sizeof(float);
+  se_fc_kernel<<<B, kThreads, smem, st>>>(pool, inv_count, w1, b1, w2, b2, gate, hidden_out, C, S);
+  EAT_CHECK_LAUNCH();
+  return EAT_OK;
+}
+
+}  // extern "C"

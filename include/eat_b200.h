@@ -1,0 +1,116 @@
+/* libeat_b200 -- C ABI of the B200-native EfficientAT hot path (mel front end + MobileNetV3 /
+ * DyMN forward & backward).  sm_100a only; no CPU fallback.
+ *
+ * The reference (fschmid56/EfficientAT) has no FFI: its hot path is Python nn.Modules calling
+ * cuFFT / cuDNN / cuBLAS through PyTorch.  Each entry point below therefore cites the reference
+ * *module code* (file:line under the reference tree) whose library calls it replaces.  The host
+ * side (efficientat_b200/models/...) mirrors the reference's nn.Module surface and reaches these
+ * functions through ctypes with raw device pointers + the current CUDA stream.
+ *
+ * Conventions
+ *   - every function returns 0 (EAT_OK) or an EAT_ERR_* code; eat_last_error() has the text.
+ *   - all pointers are DEVICE pointers unless stated; the caller owns all memory.
+ *   - work is enqueued on `stream` and is asynchronous; no function synchronises or allocates.
+ *   - activations are NHWC: [B, F, T, C] with C innermost, dtype EAT_F32 or EAT_BF16;
+ *     parameters, BatchNorm vectors, statistics and gates are always fp32 (statistics: fp64).
+ *   - "in_scale/in_shift/in_act": optional per-channel affine + activation applied to the input
+ *     operand as it is loaded (the BatchNorm+activation of the producing layer);  NULL = none.
+ *   - "scale/shift/act": optional per-channel affine + activation applied to the result.
+ *   - "stat_sum/stat_sq": optional fp64 per-channel sum / sum of squares of the RAW result
+ *     (BatchNorm batch statistics), accumulated with atomics; caller zeroes them.
+ */
+#ifndef EAT_B200_H
+#define EAT_B200_H
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EAT_OK 0
+#define EAT_ERR_ARG 1
+#define EAT_ERR_CUDA 2
+#define EAT_ERR_UNSUPPORTED 3
+
+#define EAT_ACT_NONE 0
+#define EAT_ACT_RELU 1
+#define EAT_ACT_HSWISH 2
+
+#define EAT_F32 0
+#define EAT_BF16 1
+
+const char* eat_last_error(void);
+int eat_abi_version(void);
+int eat_device_check(int device);
+
+/* Fused log-mel front end.  Replaces AugmentMelSTFT.forward, models/preprocess.py:40-67
+ * (conv1d pre-emphasis :41, torch.stft :42-43, power :44, mel matmul :56-57, log :59, affine :65).
+ * wave [B,N] fp32 -> out [B, n_mels, 1+(N-1)/hop] fp32.  twiddle: 1024 float2 (exp(-2 pi i m/512),
+ * m<512, then exp(-2 pi i k/1024), k<512).  Filterbank as bands: fb_start/fb_len [n_mels],
+ * fb_w [max_len][n_mels] (tap-major). */
+int eat_mel_fwd(const float* wave, int B, int N, const float* window, int win_length, int hop, int n_fft,
+                const float* twiddle, const int* fb_start, const int* fb_len, const float* fb_w, int max_len,
+                int n_mels, float preemph, float* out, cudaStream_t stream);
+
+/* SpecAugment masking of the log-mel (training only): torchaudio Frequency/TimeMasking with
+ * iid_masks=True, models/preprocess.py:31-38,61-63.  spec [B,F,T]; band [start,end) per example. */
+int eat_mel_mask(float* spec, int B, int F, int T, const int* f_start, const int* f_end, const int* t_start,
+                 const int* t_end, float fill, cudaStream_t stream);
+
+/* Stem 3x3 conv on the 1-channel spectrogram.  Replaces ConvNormActivation(1, C, k=3, s=2) at
+ * models/mn/model.py:125-133 (dymn/model.py:80-87).  x [B,F,T] fp32 -> out [B,Fo,To,C]. */
+int eat_stem_fwd(const float* x, const float* w, void* out, int out_dtype, int B, int F, int T, int C, int stride,
+                 const float* scale, const float* shift, int act, double* stat_sum, double* stat_sq,
+                 cudaStream_t stream);
+
+/* Depthwise weights [C,1,k,k] -> tap-major [k*k][C]. */
+int eat_dw_repack(const float* w, float* wt, int C, int k, cudaStream_t stream);
+
+/* Depthwise k x k conv (k in {3,5}, stride in {1,2}, pad (k-1)/2) + BN/act (+ SE squeeze sums).
+ * Replaces the depthwise ConvNormActivation at models/mn/block_types.py:150-162 and the mean of
+ * SqueezeExcitation._scale :73 (pool [B,C] += per-sample channel sums of the result). */
+int eat_dw_conv_fwd(const void* in, const float* wt, void* out, int dtype, int B, int F, int T, int C, int k,
+                    int stride, const float* in_scale, const float* in_shift, int in_act, const float* scale,
+                    const float* shift, int act, float* pool, double* stat_sum, double* stat_sq,
+                    cudaStream_t stream);
+
+/* Eval-mode BatchNorm folding: scale = gamma / sqrt(rvar + eps), shift = beta - rmean * scale. */
+int eat_bn_fold(const float* gamma, const float* beta, const float* rmean, const float* rvar, float eps,
+                float* scale, float* shift, int C, cudaStream_t stream);
+
+/* Training-mode BatchNorm: batch statistics -> scale/shift, saved mean/invstd, running-stat update
+ * (nn.BatchNorm2d(eps=1e-3, momentum=0.01), models/mn/model.py:114-115). rmean/rvar/nbt may be NULL. */
+int eat_bn_finalize(const double* sum, const double* sq, double count, const float* gamma, const float* beta,
+                    float eps, float momentum, float* rmean, float* rvar, long long* nbt, float* scale,
+                    float* shift, float* save_mean, float* save_invstd, int C, cudaStream_t stream);
+
+/* y = act(z * scale + shift) (+ res), elementwise on [rows, C]  (BN apply + residual,
+ * models/mn/block_types.py:177-181). */
+int eat_bn_apply(const void* z, const float* scale, const float* shift, int act, const void* res, void* y,
+                 int dtype, long long rows, int C, cudaStream_t stream);
+
+/* pool[b,c] += mul * sum_p act(z[b,p,c] * scale[c] + shift[c])   (SE squeeze / global average pool,
+ * models/mn/block_types.py:73, models/mn/model.py:220). */
+int eat_bn_act_pool(const void* z, const float* scale, const float* shift, int act, float* pool, float mul,
+                    int dtype, int B, int P, int C, cudaStream_t stream);
+
+/* Squeeze-excitation MLP: gate = sigmoid(W2 relu(W1 (pool*inv_count) + b1) + b2)
+ * (models/mn/block_types.py:72-83).  hidden_out [B,S] optional (saved for backward). */
+int eat_se_fc_fwd(const float* pool, float inv_count, const float* w1, const float* b1, const float* w2,
+                  const float* b2, float* gate, float* hidden_out, int B, int C, int S, cudaStream_t stream);
+
+/* Exact-fp32 CUDA-core GEMM: C[M,N] = epi(xf(A)[M,K] . W[N,K]^T).  1x1 convs on NHWC rows
+ * (models/mn/block_types.py:140-147,167-171) and the classifier Linear layers
+ * (models/mn/model.py:187-194).  gate [B,K]: SE gate of sample row/rows_per_sample. */
+int eat_gemm_simt_fwd(const void* A, int a_dtype, const float* W, void* C, int c_dtype, long long M, int N, int K,
+                      const float* in_scale, const float* in_shift, int in_act, const float* gate,
+                      int rows_per_sample, const float* scale, const float* shift, int act, const void* residual,
+                      double* stat_sum, double* stat_sq, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EAT_B200_H */
