@@ -1,0 +1,525 @@
+// Backward-pass kernels of the MobileNetV3 path (training step, reference ex_audioset.py:197
+// `loss.backward()` over models/mn/block_types.py:177-181 and models/mn/model.py:212-231).
+// BatchNorm backward is two passes over (upstream grad, saved raw conv output):
+//   reduce : s1[c] = sum dy, s2[c] = sum dy * xhat      with dy = g * act'(BN(z))
+//   apply  : dz = gamma*invstd * (dy - s1/M - xhat * s2/M)
+// where the upstream gradient may be composed on the fly, g = gA * gate[b,c] + dpool[b,c]
+// (squeeze-excitation gate and the gradient of a spatial mean), so those products are never stored.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct BnCtx {
+  const float* scale;   // gamma * invstd      [C]
+  const float* shift;   // beta - mean * scale [C]
+  const float* mean;    // [C]
+  const float* invstd;  // [C]
+  int act;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(
+    const T* __restrict__ gA, const float* __restrict__ gate, const float* __restrict__ dpool,
+    const T* __restrict__ z, BnCtx bn, int B, int P, int C, double* __restrict__ s1, double* __restrict__ s2) {
+  constexpr int V = Vec<T>::N;
+  extern __shared__ float smem[];   // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += kThreads) smem[i] = 0.f;
+  __syncthreads();
+  const int cv = C / V;
+  const int tcv = cv < kThreads ? cv : kThreads;
+  const int ppb = kThreads / tcv;
+  const int slot = threadIdx.x / tcv;
+  const int b = blockIdx.y;
+  if (slot < ppb) {
+    for (int cvi = threadIdx.x % tcv; cvi < cv; cvi += tcv) {
+      const int c0 = cvi * V;
+      float sc[V], sh[V], mu[V], is[V], gt[V], dp[V], a1[V], a2[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        sc[k] = bn.scale[c0 + k]; sh[k] = bn.shift[c0 + k]; mu[k] = bn.mean[c0 + k]; is[k] = bn.invstd[c0 + k];
+        gt[k] = gate != nullptr ? gate[(size_t)b * C + c0 + k] : 1.f;
+        dp[k] = dpool != nullptr ? dpool[(size_t)b * C + c0 + k] : 0.f;
+        a1[k] = 0.f; a2[k] = 0.f;
+      }
+      for (int p = blockIdx.x * ppb + slot; p < P; p += gridDim.x * ppb) {
+        const size_t off = ((size_t)b * P + p) * C + c0;
+        float zv[V], gv[V];
+        Vec<T>::load(z + off, zv);
+        if (gA != nullptr) Vec<T>::load(gA + off, gv);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          float g = (gA != nullptr ? gv[k] * gt[k] : 0.f) + dp[k];
+          float dy = g * act_bwd(fmaf(zv[k], sc[k], sh[k]), bn.act);
+          a1[k] += dy;
+          a2[k] = fmaf(dy, (zv[k] - mu[k]) * is[k], a2[k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < V; ++k) { atomicAdd(&smem[c0 + k], a1[k]); atomicAdd(&smem[C + c0 + k], a2[k]); }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kThreads) {
+    atomicAdd(s1 + c, (double)smem[c]);
+    atomicAdd(s2 + c, (double)smem[C + c]);
+  }
+}
+
+// dgamma += s2, dbeta += s1, coef = (s1/M, s2/M)
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ s1, const double* __restrict__ s2, double count,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       float* __restrict__ c1, float* __restrict__ c2, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    if (dgamma != nullptr) dgamma[c] += (float)s2[c];
+    if (dbeta != nullptr) dbeta[c] += (float)s1[c];
+    c1[c] = (float)(s1[c] / count);
+    c2[c] = (float)(s2[c] / count);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(
+    const T* __restrict__ gA, const float* __restrict__ gate, const float* __restrict__ dpool,
+    const T* __restrict__ z, BnCtx bn, const float* __restrict__ c1, const float* __restrict__ c2,
+    T* __restrict__ dz, int B, int P, int C) {
+  constexpr int V = Vec<T>::N;
+  const int cv = C / V;
+  const long long nvec = (long long)B * P * cv;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += (long long)gridDim.x * kThreads) {
+    const int c0 = (int)(i % cv) * V;
+    const int b = (int)(i / ((long long)P * cv));
+    float zv[V], gv[V], o[V];
+    Vec<T>::load(z + i * V, zv);
+    if (gA != nullptr) Vec<T>::load(gA + i * V, gv);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const int c = c0 + k;
+      float g = (gA != nullptr ? gv[k] * (gate != nullptr ? gate[(size_t)b * C + c] : 1.f) : 0.f) +
+                (dpool != nullptr ? dpool[(size_t)b * C + c] : 0.f);
+      float sc = bn.scale[c];
+      float dy = g * act_bwd(fmaf(zv[k], sc, bn.shift[c]), bn.act);
+      float xhat = (zv[k] - bn.mean[c]) * bn.invstd[c];
+      o[k] = sc * (dy - c1[c] - xhat * c2[c]);
+    }
+    Vec<T>::store(dz + i * V, o);
+  }
+}
+
+// dgate[b,c] += sum_p dp[b,p,c] * act(z[b,p,c] * scale[c] + shift[c])
+template <typename T>
+__global__ void __launch_bounds__(kThreads) se_bwd_reduce_kernel(const T* __restrict__ dp, const T* __restrict__ z,
+                                                                 const float* __restrict__ scale,
+                                                                 const float* __restrict__ shift, int act,
+                                                                 float* __restrict__ dgate, int P, int C) {
+  constexpr int V = Vec<T>::N;
+  extern __shared__ float smem[];
+  for (int i = threadIdx.x; i < C; i += kThreads) smem[i] = 0.f;
+  __syncthreads();
+  const int cv = C / V;
+  const int tcv = cv < kThreads ? cv : kThreads;
+  const int ppb = kThreads / tcv;
+  const int slot = threadIdx.x / tcv;
+  const int b = blockIdx.y;
+  if (slot < ppb) {
+    for (int cvi = threadIdx.x % tcv; cvi < cv; cvi += tcv) {
+      const int c0 = cvi * V;
+      float acc[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] = 0.f;
+      for (int p = blockIdx.x * ppb + slot; p < P; p += gridDim.x * ppb) {
+        const size_t off = ((size_t)b * P + p) * C + c0;
+        float zv[V], gv[V];
+        Vec<T>::load(z + off, zv);
+        Vec<T>::load(dp + off, gv);
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] = fmaf(gv[k], act_fwd(fmaf(zv[k], scale[c0 + k], shift[c0 + k]), act), acc[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < V; ++k) atomicAdd(&smem[c0 + k], acc[k]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kThreads) atomicAdd(dgate + (size_t)b * C + c, smem[c]);
+}
+
+// Squeeze-excitation MLP backward for one sample per CTA (block_types.py:72-83):
+//   du2 = dgate * gate * (1 - gate); dh = W2^T du2; du1 = dh * (hidden > 0); dmean = W1^T du1
+//   dpool_out[b,c] = dmean * inv_count.   du2 / du1 are stored for the weight-gradient GEMMs.
+__global__ void __launch_bounds__(kThreads) se_fc_bwd_kernel(const float* __restrict__ dgate,
+                                                             const float* __restrict__ gate,
+                                                             const float* __restrict__ hidden,
+                                                             const float* __restrict__ w1, const float* __restrict__ w2,
+                                                             float inv_count, float* __restrict__ du2,
+                                                             float* __restrict__ du1, float* __restrict__ dpool,
+                                                             int C, int S) {
+  extern __shared__ float smem[];
+  float* s_du2 = smem;       // [C]
+  float* s_du1 = smem + C;   // [S]
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += kThreads) {
+    float g = gate[(size_t)b * C + c];
+    float v = dgate[(size_t)b * C + c] * g * (1.f - g);
+    s_du2[c] = v;
+    du2[(size_t)b * C + c] = v;
+  }
+  __syncthreads();
+  // dh[s] = sum_c w2[c, s] * du2[c]   (column access of w2: threads over s are coalesced)
+  for (int s = threadIdx.x; s < S; s += kThreads) {
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c) acc = fmaf(__ldg(w2 + (size_t)c * S + s), s_du2[c], acc);
+    float v = hidden[(size_t)b * S + s] > 0.f ? acc : 0.f;
+    s_du1[s] = v;
+    du1[(size_t)b * S + s] = v;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kThreads) {
+    float acc = 0.f;
+    for (int s = 0; s < S; ++s) acc = fmaf(__ldg(w1 + (size_t)s * C + c), s_du1[s], acc);
+    dpool[(size_t)b * C + c] = acc * inv_count;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Depthwise conv backward.  dgrad: gather over output pixels that read this input pixel.
+template <typename T, int K, int S>
+__global__ void __launch_bounds__(kThreads) dw_dgrad_kernel(const T* __restrict__ dz, const float* __restrict__ wt,
+                                                            const T* __restrict__ res, T* __restrict__ din,
+                                                            int F, int Tn, int Fo, int To, int C) {
+  constexpr int V = Vec<T>::N;
+  constexpr int PAD = (K - 1) / 2;
+  const int cv = C / V;
+  const int b = blockIdx.y;
+  const long long nvec = (long long)F * Tn * cv;
+  const T* dzb = dz + (size_t)b * Fo * To * C;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += (long long)gridDim.x * kThreads) {
+    const int c0 = (int)(i % cv) * V;
+    const int t = (int)((i / cv) % Tn);
+    const int f = (int)(i / ((long long)cv * Tn));
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+      const int nf = f + PAD - ky;
+      if (nf < 0 || nf % S != 0) continue;
+      const int fo = nf / S;
+      if (fo >= Fo) continue;
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const int nt = t + PAD - kx;
+        if (nt < 0 || nt % S != 0) continue;
+        const int to = nt / S;
+        if (to >= To) continue;
+        float g[V];
+        Vec<T>::load(dzb + ((size_t)fo * To + to) * C + c0, g);
+        const float4* wp = reinterpret_cast<const float4*>(wt + (size_t)(ky * K + kx) * C + c0);
+#pragma unroll
+        for (int q = 0; q < V / 4; ++q) {
+          float4 w4 = __ldg(wp + q);
+          acc[4 * q] = fmaf(g[4 * q], w4.x, acc[4 * q]);
+          acc[4 * q + 1] = fmaf(g[4 * q + 1], w4.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(g[4 * q + 2], w4.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(g[4 * q + 3], w4.w, acc[4 * q + 3]);
+        }
+      }
+    }
+    const size_t off = (size_t)b * F * Tn * C + (size_t)i * V;
+    if (res != nullptr) {
+      float r[V];
+      Vec<T>::load(res + off, r);
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] += r[k];
+    }
+    Vec<T>::store(din + off, acc);
+  }
+}
+
+// wgrad: dw[c, ky, kx] += sum_{b, fo, to} dz[b,fo,to,c] * xf(in)[b, fo*S-PAD+ky, to*S-PAD+kx, c]
+// thread = (pixel slot, channel vector), K*K*V register accumulators, shared + global atomics at the end.
+template <typename T, int K, int S>
+__global__ void __launch_bounds__(kThreads) dw_wgrad_kernel(const T* __restrict__ dz, const T* __restrict__ in,
+                                                            InXform xf, float* __restrict__ dw /*[C,1,K,K]*/,
+                                                            int F, int Tn, int Fo, int To, int C) {
+  constexpr int V = Vec<T>::N;
+  constexpr int PAD = (K - 1) / 2;
+  constexpr int KK = K * K;
+  extern __shared__ float smem[];   // [KK][C]
+  for (int i = threadIdx.x; i < KK * C; i += kThreads) smem[i] = 0.f;
+  __syncthreads();
+  const int cv = C / V;
+  const int tcv = cv < kThreads ? cv : kThreads;
+  const int ppb = kThreads / tcv;
+  const int slot = threadIdx.x / tcv;
+  const int b = blockIdx.y;
+  const T* inb = in + (size_t)b * F * Tn * C;
+  const T* dzb = dz + (size_t)b * Fo * To * C;
+  const int npix = Fo * To;
+  if (slot < ppb) {
+    for (int cvi = threadIdx.x % tcv; cvi < cv; cvi += tcv) {
+      const int c0 = cvi * V;
+      float isc[V], ish[V];
+      if (xf.scale != nullptr) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) { isc[k] = xf.scale[c0 + k]; ish[k] = xf.shift[c0 + k]; }
+      }
+      // one kernel row at a time keeps the accumulators at K*V registers (25*8 would spill)
+      for (int ky = 0; ky < K; ++ky) {
+        float acc[K][V];
+#pragma unroll
+        for (int q = 0; q < K; ++q)
+#pragma unroll
+          for (int k = 0; k < V; ++k) acc[q][k] = 0.f;
+        for (int p = blockIdx.x * ppb + slot; p < npix; p += gridDim.x * ppb) {
+          const int fo = p / To, to = p - fo * To;
+          const int f = fo * S - PAD + ky;
+          if (f < 0 || f >= F) continue;
+          float g[V];
+          Vec<T>::load(dzb + (size_t)p * C + c0, g);
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) {
+            const int t = to * S - PAD + kx;
+            if (t < 0 || t >= Tn) continue;
+            float v[V];
+            Vec<T>::load(inb + ((size_t)f * Tn + t) * C + c0, v);
+            if (xf.scale != nullptr) {
+#pragma unroll
+              for (int k = 0; k < V; ++k) v[k] = act_fwd(fmaf(v[k], isc[k], ish[k]), xf.act);
+            }
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[kx][k] = fmaf(g[k], v[k], acc[kx][k]);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < K; ++q)
+#pragma unroll
+          for (int k = 0; k < V; ++k) atomicAdd(&smem[(ky * K + q) * C + c0 + k], acc[q][k]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < KK * C; i += kThreads) {
+    const int q = i / C, c = i % C;
+    atomicAdd(dw + (size_t)c * KK + q, smem[i]);
+  }
+}
+
+// stem wgrad: dw[c, ky, kx] += sum dz[b,fo,to,c] * x[b, fo*s-1+ky, to*s-1+kx]
+template <typename T>
+__global__ void __launch_bounds__(kThreads) stem_wgrad_kernel(const T* __restrict__ dz, const float* __restrict__ x,
+                                                              float* __restrict__ dw, int B, int F, int Tn, int Fo,
+                                                              int To, int C, int stride) {
+  constexpr int V = Vec<T>::N;
+  extern __shared__ float smem[];   // [9][C]
+  for (int i = threadIdx.x; i < 9 * C; i += kThreads) smem[i] = 0.f;
+  __syncthreads();
+  const int cv = C / V;
+  const int ppb = kThreads / cv;
+  const int cvi = threadIdx.x % cv, slot = threadIdx.x / cv;
+  const long long npix = (long long)B * Fo * To;
+  if (slot < ppb) {
+    float acc[9][V];
+#pragma unroll
+    for (int q = 0; q < 9; ++q)
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[q][k] = 0.f;
+    for (long long pix = (long long)blockIdx.x * ppb + slot; pix < npix; pix += (long long)gridDim.x * ppb) {
+      const int to = (int)(pix % To), fo = (int)((pix / To) % Fo), b = (int)(pix / ((long long)To * Fo));
+      float g[V];
+      Vec<T>::load(dz + (size_t)pix * C + cvi * V, g);
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int f = fo * stride - 1 + ky;
+        if (f < 0 || f >= F) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int t = to * stride - 1 + kx;
+          if (t < 0 || t >= Tn) continue;
+          const float xv = __ldg(x + ((size_t)b * F + f) * Tn + t);
+#pragma unroll
+          for (int k = 0; k < V; ++k) acc[ky * 3 + kx][k] = fmaf(g[k], xv, acc[ky * 3 + kx][k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 9; ++q)
+#pragma unroll
+      for (int k = 0; k < V; ++k) atomicAdd(&smem[q * C + cvi * V + k], acc[q][k]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 9 * C; i += kThreads) {
+    const int q = i / C, c = i % C;
+    atomicAdd(dw + (size_t)c * 9 + q, smem[i]);
+  }
+}
+
+// head: dpre = dh * mask * act'(pre)   (fp32, [n])
+__global__ void act_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ pre,
+                               const float* __restrict__ mask, int act, float* __restrict__ dpre, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dpre[i] = dh[i] * (mask != nullptr ? mask[i] : 1.f) * act_bwd(pre[i], act);
+}
+
+inline int grid2(int P, int ppb, int B) {
+  int gx = ceil_div(P, ppb * 4);
+  const int cap = max(1, (148 * 8) / max(B, 1));
+  if (gx > cap) gx = cap;
+  return gx < 1 ? 1 : gx;
+}
+
+template <typename T>
+int launch_bn_bwd_reduce(const void* gA, const float* gate, const float* dpool, const void* z, BnCtx bn, int B, int P,
+                         int C, double* s1, double* s2, cudaStream_t st) {
+  constexpr int V = Vec<T>::N;
+  const int cv = C / V, tcv = cv < kThreads ? cv : kThreads, ppb = kThreads / tcv;
+  dim3 grid(grid2(P, ppb, B), B);
+  bn_bwd_reduce_kernel<T><<<grid, kThreads, 2 * C * sizeof(float), st>>>((const T*)gA, gate, dpool, (const T*)z, bn, B, P, C, s1, s2);
+  EAT_CHECK_LAUNCH();
+  return EAT_OK;
+}
+
+template <typename T>
+int launch_dw_bwd(int which, const void* dz, const float* wt, const void* in, InXform xf, const void* res, void* din,
+                  float* dw, int B, int F, int Tn, int C, int k, int stride, cudaStream_t st) {
+  constexpr int V = Vec<T>::N;
+  if (C % V != 0) { eat_set_error("dw bwd: channels must be a multiple of the vector width"); return EAT_ERR_ARG; }
+  const int pad = (k - 1) / 2;
+  const int Fo = (F + 2 * pad - k) / stride + 1, To = (Tn + 2 * pad - k) / stride + 1;
+  const int cv = C / V;
+  if (which == 0) {
+    long long nvec = (long long)F * Tn * cv;
+    int gx = (int)min((long long)max(1, (148 * 16) / max(B, 1)), ceil_div_ll(nvec, kThreads));
+    dim3 grid(gx < 1 ? 1 : gx, B);
+#define EAT_DG(KK, SS) dw_dgrad_kernel<T, KK, SS><<<grid, kThreads, 0, st>>>((const T*)dz, wt, (const T*)res, (T*)din, F, Tn, Fo, To, C)
+    if (k == 3 && stride == 1) EAT_DG(3, 1); else if (k == 3 && stride == 2) EAT_DG(3, 2);
+    else if (k == 5 && stride == 1) EAT_DG(5, 1); else if (k == 5 && stride == 2) EAT_DG(5, 2);
+    else { eat_set_error("dw dgrad: only k in {3,5}, stride in {1,2}"); return EAT_ERR_UNSUPPORTED; }
+#undef EAT_DG
+  } else {
+    const int tcv = cv < kThreads ? cv : kThreads, ppb = kThreads / tcv;
+    dim3 grid(grid2(Fo * To, ppb, B), B);
+    size_t smem = (size_t)k * k * C * sizeof(float);
+    if (smem > 200 * 1024) { eat_set_error("dw wgrad: channel count too large for the shared accumulator"); return EAT_ERR_UNSUPPORTED; }
+#define EAT_WG(KK, SS)                                                                                         \
+  do {                                                                                                         \
+    cudaFuncSetAttribute(dw_wgrad_kernel<T, KK, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+    dw_wgrad_kernel<T, KK, SS><<<grid, kThreads, smem, st>>>((const T*)dz, (const T*)in, xf, dw, F, Tn, Fo, To, C); \
+  } while (0)
+    if (k == 3 && stride == 1) EAT_WG(3, 1); else if (k == 3 && stride == 2) EAT_WG(3, 2);
+    else if (k == 5 && stride == 1) EAT_WG(5, 1); else if (k == 5 && stride == 2) EAT_WG(5, 2);
+    else { eat_set_error("dw wgrad: only k in {3,5}, stride in {1,2}"); return EAT_ERR_UNSUPPORTED; }
+#undef EAT_WG
+  }
+  EAT_CHECK_LAUNCH();
+  return EAT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int eat_bn_bwd_reduce(const void* gA, const float* gate, const float* dpool, const void* z, const float* scale,
+                      const float* shift, const float* mean, const float* invstd, int act, int dtype, int B, int P,
+                      int C, double* s1, double* s2, cudaStream_t st) {
+  if (B == 0 || P == 0) return EAT_OK;
+  BnCtx bn{scale, shift, mean, invstd, act};
+  const int V = dtype == EAT_BF16 ? 8 : 4;
+  if (C % V != 0) { eat_set_error("bn_bwd_reduce: channels must be a multiple of the vector width"); return EAT_ERR_ARG; }
+  if (dtype == EAT_BF16) return launch_bn_bwd_reduce<__nv_bfloat16>(gA, gate, dpool, z, bn, B, P, C, s1, s2, st);
+  return launch_bn_bwd_reduce<float>(gA, gate, dpool, z, bn, B, P, C, s1, s2, st);
+}
+
+int eat_bn_bwd_finalize(const double* s1, const double* s2, double count, float* dgamma, float* dbeta, float* c1,
+                        float* c2, int C, cudaStream_t st) {
+  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(s1, s2, count, dgamma, dbeta, c1, c2, C);
+  EAT_CHECK_LAUNCH();
+  return EAT_OK;
+}
+
+int eat_bn_bwd_apply(const void* gA, const float* gate, const float* dpool, const void* z, const float* scale,
+                     const float* shift, const float* mean, const float* invstd, int act, const float* c1,
+                     const float* c2, void* dz, int dtype, int B, int P, int C, cudaStream_t st) {
+  if (B == 0 || P == 0) return EAT_OK;
+  BnCtx bn{scale, shift, mean, invstd, act};
+  const int V = dtype == EAT_BF16 ? 8 : 4;
+  if (C % V != 0) { eat_set_error("bn_bwd_apply: channels must be a multiple of the vector width"); return EAT_ERR_ARG; }
+  long long nvec = (long long)B * P * (C / V);
+  int grid = (int)min((long long)148 * 16, ceil_div_ll(nvec, kThreads));
+  if (dtype == EAT_BF16)
+    bn_bwd_apply_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)gA, gate, dpool, (const __nv_bfloat16*)z, bn, c1, c2, (__nv_bfloat16*)dz, B, P, C);
+  else
+    bn_bwd_apply_kernel<float><<<grid, kThreads, 0, st>>>((const float*)gA, gate, dpool, (const float*)z, bn, c1, c2, (float*)dz, B, P, C);
+  EAT_CHECK_LAUNCH();
+  return EAT_OK;
+}
+
+int eat_se_bwd_reduce(const void* dp, const void* z, const float* scale, const float* shift, int act, float* dgate,
+                      int dtype, int B, int P, int C, cudaStream_t st) {
+  if (B == 0) return EAT_OK;
+  const int V = dtype == EAT_BF16 ? 8 : 4;
+  if (C % V != 0) { eat_set_error("se_bwd_reduce: channels must be a multiple of the vector width"); return EAT_ERR_ARG; }
+  const int cv = C / V, tcv = cv < kThreads ? cv : kThreads, ppb = kThreads / tcv;
+  dim3 grid(grid2(P, ppb, B), B);
+  if (dtype == EAT_BF16)
+    se_bwd_reduce_kernel<__nv_bfloat16><<<grid, kThreads, C * sizeof(float), st>>>((const __nv_bfloat16*)dp, (const __nv_bfloat16*)z, scale, shift, act, dgate, P, C);
+  else
+    se_bwd_reduce_kernel<float><<<grid, kThreads, C * sizeof(float), st>>>((const float*)dp, (const float*)z, scale, shift, act, dgate, P, C);
+  EAT_CHECK_LAUNCH();
+  return EAT_OK;
+}
+
+int eat_se_fc_bwd(const float* dgate, const float* gate, const float* hidden, const float* w1, const float* w2,
+                  float inv_count, float* du2, float* du1, float* dpool, int B, int C, int S, cudaStream_t st) {
+  if (B == 0) return EAT_OK;
+  se_fc_bwd_kernel<<<B, kThreads, (size_t)(C + S) * sizeof(float), st>>>(dgate, gate, hidden, w1, w2, inv_count, du2, du1, dpool, C, S);
+  EAT_CHECK_LAUNCH();
+  return EAT_OK;
+}
+
+int eat_dw_conv_dgrad(const void* dz, const float* wt, const void* res, void* din, int dtype, int B, int F, int T,
+                      int C, int k, int stride, cudaStream_t st) {
+  if (B == 0) return EAT_OK;
+  InXform xf{nullptr, nullptr, nullptr, 0, 0};
+  if (dtype == EAT_BF16) return launch_dw_bwd<__nv_bfloat16>(0, dz, wt, nullptr, xf, res, din, nullptr, B, F, T, C, k, stride, st);
+  return launch_dw_bwd<float>(0, dz, wt, nullptr, xf, res, din, nullptr, B, F, T, C, k, stride, st);
+}
+
+int eat_dw_conv_wgrad(const void* dz, const void* in, const float* in_scale, const float* in_shift, int in_act,
+                      float* dw, int dtype, int B, int F, int T, int C, int k, int stride, cudaStream_t st) {
+  if (B == 0) return EAT_OK;
+  InXform xf{in_scale, in_shift, nullptr, in_act, 0};
+  if (dtype == EAT_BF16) return launch_dw_bwd<__nv_bfloat16>(1, dz, nullptr, in, xf, nullptr, nullptr, dw, B, F, T, C, k, stride, st);
+  return launch_dw_bwd<float>(1, dz, nullptr, in, xf, nullptr, nullptr, dw, B, F, T, C, k, stride, st);
+}
+
+int eat_stem_wgrad(const void* dz, int dtype, const float* x, float* dw, int B, int F, int T, int C, int stride,
+                   cudaStream_t st) {
+  const int Fo = (F + 2 - 3) / stride + 1, To = (T + 2 - 3) / stride + 1;
+  const int V = dtype == EAT_BF16 ? 8 : 4;
+  if (C % V != 0 || C / V > kThreads) { eat_set_error("stem wgrad: unsupported channel count"); return EAT_ERR_ARG; }
+  const long long npix = (long long)B * Fo * To;
+  if (npix == 0) return EAT_OK;
+  const int ppb = kThreads / (C / V);
+  int grid = (int)min((long long)148 * 4, ceil_div_ll(npix, ppb * 8));
+  if (grid < 1) grid = 1;
+  size_t smem = (size_t)9 * C * sizeof(float);
+  if (dtype == EAT_BF16)
+    stem_wgrad_kernel<__nv_bfloat16><<<grid, kThreads, smem, st>>>((const __nv_bfloat16*)dz, x, dw, B, F, T, Fo, To, C, stride);
+  else
+    stem_wgrad_kernel<float><<<grid, kThreads, smem, st>>>((const float*)dz, x, dw, B, F, T, Fo, To, C, stride);
+  EAT_CHECK_LAUNCH();
+  return EAT_OK;
+}
+
+int eat_act_bwd(const float* dh, const float* pre, const float* mask, int act, float* dpre, long long n,
+                cudaStream_t st) {
+  if (n == 0) return EAT_OK;
+  int grid = (int)min((long long)148 * 8, ceil_div_ll(n, 256));
+  act_bwd_kernel<<<grid, 256, 0, st>>>(dh, pre, mask, act, dpre, n);
+  EAT_CHECK_LAUNCH();
+  return EAT_OK;
+}
+
+}  // extern "C"

@@ -92,20 +92,20 @@ class MNEngine:
 
     # ------------------------------------------------------------------ kernel wrappers
     def _gemm(self, a, w, out, M, N, K, in_sc=None, in_act=0, gate=None, rows_per_sample=1, sc=None, bias=None,
-              act=0, res=None, stats=None, a_code=None, c_code=None):
+              act=0, res=None, stats=None, a_code=None, c_code=None, w_trans=False):
         """out[M,N] = epi(xf(a)[M,K] . w[N,K]^T).  in_sc: [2,K] (scale, shift) or None; sc: [2,N] or None;
         bias: [N] used as shift with scale None."""
         a_code = self.dcode if a_code is None else a_code
         c_code = self.dcode if c_code is None else c_code
         scale = _ptr(sc[0]) if sc is not None else 0
         shift = _ptr(sc[1]) if sc is not None else _ptr(bias)
-        args = (a.data_ptr(), a_code, w.data_ptr(), out.data_ptr(), c_code, M, N, K,
+        args = (a.data_ptr(), a_code, w.data_ptr(), 1 if w_trans else 0, out.data_ptr(), c_code, M, N, K,
                 _ptr(in_sc[0]) if in_sc is not None else 0, _ptr(in_sc[1]) if in_sc is not None else 0, in_act,
                 _ptr(gate), rows_per_sample, scale, shift, act, _ptr(res),
                 _ptr(stats[0]) if stats is not None else 0, _ptr(stats[1]) if stats is not None else 0, _stream())
         L = lib()
         use_tc = self.gemm_impl == "tc" or (self.gemm_impl == "auto" and hasattr(L, "pw_tc_fwd") and
-                                            a_code == c_code and M >= 128 and K % 8 == 0 and N % 8 == 0)
+                                            a_code == c_code and not w_trans and M >= 128 and K % 8 == 0 and N % 8 == 0)
         if use_tc and hasattr(L, "pw_tc_fwd"):
             L.pw_tc_fwd(*args)
         else:
@@ -227,3 +227,236 @@ class MNEngine:
         self._gemm(h, self.fc2.weight, logits, B, self.fc2.out_features, self.fc1.out_features, bias=self.fc2.bias,
                    a_code=0, c_code=0)
         return logits, feat, fmaps
+
+    # ------------------------------------------------------------------ training forward
+    def _new_stats(self, c, dev):
+        return torch.zeros(2, c, device=dev, dtype=torch.float64)
+
+    def _forward_train(self, x, dropout_mask=None):
+        """Batch-statistics forward.  Returns (logits, feat, saved) where `saved` holds the raw conv outputs
+        and BatchNorm statistics needed by `_backward` (activations are recomputed from them)."""
+        L = lib()
+        dev = x.device
+        st = _stream()
+        td, dc = self.tdtype, self.dcode
+        x = x.detach().float().contiguous()
+        B, _, F, T = x.shape
+        HS = ACT["hswish"]
+        S = {"x": x, "B": B, "F": F, "T": T, "blocks": []}
+
+        conv, bn = self.stem[0], self.stem[1]
+        s0 = conv.stride[0]
+        Fi, Ti = _conv_out(F, 3, s0), _conv_out(T, 3, s0)
+        c0 = conv.out_channels
+        z0 = torch.empty(B, Fi, Ti, c0, device=dev, dtype=td)
+        stt = self._new_stats(c0, dev)
+        L.stem_fwd(x.data_ptr(), conv.weight.data_ptr(), z0.data_ptr(), dc, B, F, T, c0, s0, 0, 0, 0,
+                   stt[0].data_ptr(), stt[1].data_ptr(), st)
+        sc0, sv0 = self._finalize(bn, stt, B * Fi * Ti, dev)
+        a = torch.empty_like(z0)
+        L.bn_apply(z0.data_ptr(), sc0[0].data_ptr(), sc0[1].data_ptr(), HS, 0, a.data_ptr(), dc, B * Fi * Ti, c0, st)
+        S["stem"] = dict(z=z0, sc=sc0, sv=sv0, Fo=Fi, To=Ti)
+        for blk in self.blocks:
+            R = {"inp": a, "Fi": Fi, "Ti": Ti}
+            inp = a
+            M = B * Fi * Ti
+            if blk.expand is not None:
+                z1 = torch.empty(B, Fi, Ti, blk.cexp, device=dev, dtype=td)
+                stt = self._new_stats(blk.cexp, dev)
+                self._gemm(inp, blk.expand[0].weight, z1, M, blk.cexp, blk.cin, stats=stt)
+                sc1, sv1 = self._finalize(blk.expand[1], stt, M, dev)
+                R.update(z1=z1, sc1=sc1, sv1=sv1)
+                dw_in, dw_sc = z1, sc1
+            else:
+                dw_in, dw_sc = inp, None
+            Fo, To = _conv_out(Fi, blk.k, blk.stride), _conv_out(Ti, blk.k, blk.stride)
+            Mo = B * Fo * To
+            z2 = torch.empty(B, Fo, To, blk.cexp, device=dev, dtype=td)
+            stt = self._new_stats(blk.cexp, dev)
+            wt = self._dw_weights(blk.dw[0], dev)
+            L.dw_conv_fwd(dw_in.data_ptr(), wt.data_ptr(), z2.data_ptr(), dc, B, Fi, Ti, blk.cexp, blk.k, blk.stride,
+                          _ptr(dw_sc[0]) if dw_sc is not None else 0, _ptr(dw_sc[1]) if dw_sc is not None else 0,
+                          blk.act if dw_sc is not None else 0, 0, 0, 0, 0, stt[0].data_ptr(), stt[1].data_ptr(), st)
+            sc2, sv2 = self._finalize(blk.dw[1], stt, Mo, dev)
+            R.update(z2=z2, sc2=sc2, sv2=sv2, wt=wt, Fo=Fo, To=To)
+            gate = None
+            if blk.se is not None:
+                Sq = blk.se.fc1.out_features
+                pool = torch.zeros(B, blk.cexp, device=dev, dtype=torch.float32)
+                L.bn_act_pool(z2.data_ptr(), sc2[0].data_ptr(), sc2[1].data_ptr(), blk.act, pool.data_ptr(),
+                              1.0 / (Fo * To), dc, B, Fo * To, blk.cexp, st)
+                gate = torch.empty(B, blk.cexp, device=dev, dtype=torch.float32)
+                hidden = torch.empty(B, Sq, device=dev, dtype=torch.float32)
+                L.se_fc_fwd(pool.data_ptr(), 1.0, blk.se.fc1.weight.data_ptr(), blk.se.fc1.bias.data_ptr(),
+                            blk.se.fc2.weight.data_ptr(), blk.se.fc2.bias.data_ptr(), gate.data_ptr(),
+                            hidden.data_ptr(), B, blk.cexp, Sq, st)
+                R.update(mean=pool, gate=gate, hidden=hidden)
+            z3 = torch.empty(B, Fo, To, blk.cout, device=dev, dtype=td)
+            stt = self._new_stats(blk.cout, dev)
+            self._gemm(z2, blk.proj[0].weight, z3, Mo, blk.cout, blk.cexp, in_sc=sc2, in_act=blk.act, gate=gate,
+                       rows_per_sample=Fo * To, stats=stt)
+            sc3, sv3 = self._finalize(blk.proj[1], stt, Mo, dev)
+            a = torch.empty(B, Fo, To, blk.cout, device=dev, dtype=td)
+            L.bn_apply(z3.data_ptr(), sc3[0].data_ptr(), sc3[1].data_ptr(), 0, _ptr(inp) if blk.res else 0,
+                       a.data_ptr(), dc, Mo, blk.cout, st)
+            R.update(z3=z3, sc3=sc3, sv3=sv3)
+            S["blocks"].append(R)
+            Fi, Ti = Fo, To
+        conv, bn = self.last[0], self.last[1]
+        cl = conv.out_channels
+        M = B * Fi * Ti
+        zl = torch.empty(B, Fi, Ti, cl, device=dev, dtype=td)
+        stt = self._new_stats(cl, dev)
+        self._gemm(a, conv.weight, zl, M, cl, conv.in_channels, stats=stt)
+        scl, svl = self._finalize(bn, stt, M, dev)
+        feat = torch.zeros(B, cl, device=dev, dtype=torch.float32)
+        L.bn_act_pool(zl.data_ptr(), scl[0].data_ptr(), scl[1].data_ptr(), HS, feat.data_ptr(), 1.0 / (Fi * Ti), dc, B,
+                      Fi * Ti, cl, st)
+        S["last"] = dict(inp=a, z=zl, sc=scl, sv=svl, Fi=Fi, Ti=Ti)
+        # classifier: Linear -> Hardswish -> Dropout -> Linear.  The Hardswish and the dropout mask are applied on
+        # the operand load of the second GEMM (in_act + per-row gate), so only the pre-activation is stored.
+        n1 = self.fc1.out_features
+        h_pre = torch.empty(B, n1, device=dev, dtype=torch.float32)
+        self._gemm(feat, self.fc1.weight, h_pre, B, n1, cl, bias=self.fc1.bias, a_code=0, c_code=0)
+        p = self.dropout_p
+        if dropout_mask is None and p > 0:
+            dropout_mask = torch.empty(B, n1, device=dev, dtype=torch.float32).bernoulli_(1.0 - p).div_(1.0 - p)
+        ident = self._ident(n1, dev)
+        logits = torch.empty(B, self.fc2.out_features, device=dev, dtype=torch.float32)
+        self._gemm(h_pre, self.fc2.weight, logits, B, self.fc2.out_features, n1, in_sc=ident, in_act=HS,
+                   gate=dropout_mask, rows_per_sample=1, bias=self.fc2.bias, a_code=0, c_code=0)
+        S["head"] = dict(feat=feat, h_pre=h_pre, mask=dropout_mask, ident=ident)
+        return logits, feat, S
+
+    def _ident(self, n, dev):
+        t = torch.empty(2, n, device=dev, dtype=torch.float32)
+        t[0].fill_(1.0)
+        t[1].zero_()
+        return t
+
+    # ------------------------------------------------------------------ backward
+    def param_list(self):
+        return [p for p in self.model.parameters()]
+
+    def _wgrad(self, g, a, dW, db, M, N, K, in_sc=None, in_act=0, gate=None, rows_per_sample=1, g_code=None,
+               a_code=None):
+        g_code = self.dcode if g_code is None else g_code
+        a_code = self.dcode if a_code is None else a_code
+        lib().gemm_simt_wgrad(g.data_ptr(), g_code, a.data_ptr(), a_code, dW.data_ptr(), _ptr(db), M, N, K,
+                              _ptr(in_sc[0]) if in_sc is not None else 0, _ptr(in_sc[1]) if in_sc is not None else 0,
+                              in_act, _ptr(gate), rows_per_sample, _stream())
+
+    def _bn_bwd(self, gA, gate, dpool, z, sc, sv, act, B, P, C, dgamma, dbeta, dev):
+        """two-pass BatchNorm(+activation) backward -> dz (same dtype/shape as z)."""
+        L = lib()
+        st = _stream()
+        s = torch.zeros(2, C, device=dev, dtype=torch.float64)
+        L.bn_bwd_reduce(_ptr(gA), _ptr(gate), _ptr(dpool), z.data_ptr(), sc[0].data_ptr(), sc[1].data_ptr(),
+                        sv[0].data_ptr(), sv[1].data_ptr(), act, self.dcode, B, P, C, s[0].data_ptr(), s[1].data_ptr(), st)
+        coef = torch.empty(2, C, device=dev, dtype=torch.float32)
+        L.bn_bwd_finalize(s[0].data_ptr(), s[1].data_ptr(), float(B * P), _ptr(dgamma), _ptr(dbeta),
+                          coef[0].data_ptr(), coef[1].data_ptr(), C, st)
+        dz = torch.empty_like(z)
+        L.bn_bwd_apply(_ptr(gA), _ptr(gate), _ptr(dpool), z.data_ptr(), sc[0].data_ptr(), sc[1].data_ptr(),
+                       sv[0].data_ptr(), sv[1].data_ptr(), act, coef[0].data_ptr(), coef[1].data_ptr(), dz.data_ptr(),
+                       self.dcode, B, P, C, st)
+        return dz
+
+    def _backward(self, S, dlogits):
+        """-> dict {parameter: fp32 gradient view into one flat arena} (arena returned under key None)."""
+        L = lib()
+        st = _stream()
+        dev = dlogits.device
+        td, dc = self.tdtype, self.dcode
+        B = S["B"]
+        HS = ACT["hswish"]
+        params = self.param_list()
+        flat = torch.zeros(sum(p.numel() for p in params), device=dev, dtype=torch.float32)
+        G, off = {}, 0
+        for p in params:
+            G[p] = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        dlogits = dlogits.float().contiguous()
+
+        # ---- classifier
+        H = S["head"]
+        n1, ncls, cl = self.fc1.out_features, self.fc2.out_features, self.fc1.in_features
+        self._wgrad(dlogits, H["h_pre"], G[self.fc2.weight], G[self.fc2.bias], B, ncls, n1, in_sc=H["ident"], in_act=HS,
+                    gate=H["mask"], rows_per_sample=1, g_code=0, a_code=0)
+        dh = torch.empty(B, n1, device=dev, dtype=torch.float32)
+        self._gemm(dlogits, self.fc2.weight, dh, B, n1, ncls, a_code=0, c_code=0, w_trans=True)
+        dpre = torch.empty_like(dh)
+        L.act_bwd(dh.data_ptr(), H["h_pre"].data_ptr(), _ptr(H["mask"]), HS, dpre.data_ptr(), dh.numel(), st)
+        self._wgrad(dpre, H["feat"], G[self.fc1.weight], G[self.fc1.bias], B, n1, cl, g_code=0, a_code=0)
+        dfeat = torch.empty(B, cl, device=dev, dtype=torch.float32)
+        self._gemm(dpre, self.fc1.weight, dfeat, B, cl, n1, a_code=0, c_code=0, w_trans=True)
+
+        # ---- last 1x1 conv (+BN+Hardswish, global average pool)
+        Ls = S["last"]
+        P = Ls["Fi"] * Ls["Ti"]
+        conv, bn = self.last[0], self.last[1]
+        dpool = dfeat.mul_(1.0 / P)      # gradient of the spatial mean, broadcast inside the BN-backward kernels
+        dz = self._bn_bwd(None, None, dpool, Ls["z"], Ls["sc"], Ls["sv"], HS, B, P, cl, G[bn.weight], G[bn.bias], dev)
+        self._wgrad(dz, Ls["inp"], G[conv.weight], None, B * P, cl, conv.in_channels)
+        dy = torch.empty_like(Ls["inp"])
+        self._gemm(dz, conv.weight, dy, B * P, conv.in_channels, cl, w_trans=True)
+
+        # ---- inverted residual blocks, last to first
+        for blk, R in zip(reversed(self.blocks), reversed(S["blocks"])):
+            Fi, Ti, Fo, To = R["Fi"], R["Ti"], R["Fo"], R["To"]
+            Pi, Po = Fi * Ti, Fo * To
+            gate = R.get("gate")
+            # project: BN3 (no activation)
+            dz3 = self._bn_bwd(dy, None, None, R["z3"], R["sc3"], R["sv3"], 0, B, Po, blk.cout,
+                               G[blk.proj[1].weight], G[blk.proj[1].bias], dev)
+            self._wgrad(dz3, R["z2"], G[blk.proj[0].weight], None, B * Po, blk.cout, blk.cexp, in_sc=R["sc2"],
+                        in_act=blk.act, gate=gate, rows_per_sample=Po)
+            dp = torch.empty_like(R["z2"])
+            self._gemm(dz3, blk.proj[0].weight, dp, B * Po, blk.cexp, blk.cout, w_trans=True)
+            dpool = None
+            if blk.se is not None:
+                Sq = blk.se.fc1.out_features
+                dgate = torch.zeros(B, blk.cexp, device=dev, dtype=torch.float32)
+                L.se_bwd_reduce(dp.data_ptr(), R["z2"].data_ptr(), R["sc2"][0].data_ptr(), R["sc2"][1].data_ptr(),
+                                blk.act, dgate.data_ptr(), dc, B, Po, blk.cexp, st)
+                du2 = torch.empty(B, blk.cexp, device=dev, dtype=torch.float32)
+                du1 = torch.empty(B, Sq, device=dev, dtype=torch.float32)
+                dpool = torch.empty(B, blk.cexp, device=dev, dtype=torch.float32)
+                L.se_fc_bwd(dgate.data_ptr(), gate.data_ptr(), R["hidden"].data_ptr(), blk.se.fc1.weight.data_ptr(),
+                            blk.se.fc2.weight.data_ptr(), 1.0 / Po, du2.data_ptr(), du1.data_ptr(), dpool.data_ptr(),
+                            B, blk.cexp, Sq, st)
+                self._wgrad(du2, R["hidden"], G[blk.se.fc2.weight], G[blk.se.fc2.bias], B, blk.cexp, Sq, g_code=0, a_code=0)
+                self._wgrad(du1, R["mean"], G[blk.se.fc1.weight], G[blk.se.fc1.bias], B, Sq, blk.cexp, g_code=0, a_code=0)
+            # depthwise: BN2 + activation (+ SE gate / squeeze gradient composed on the fly)
+            dz2 = self._bn_bwd(dp, gate, dpool, R["z2"], R["sc2"], R["sv2"], blk.act, B, Po, blk.cexp,
+                               G[blk.dw[1].weight], G[blk.dw[1].bias], dev)
+            has_exp = blk.expand is not None
+            dw_in = R["z1"] if has_exp else R["inp"]
+            sc1 = R["sc1"] if has_exp else None
+            L.dw_conv_wgrad(dz2.data_ptr(), dw_in.data_ptr(), _ptr(sc1[0]) if has_exp else 0,
+                            _ptr(sc1[1]) if has_exp else 0, blk.act if has_exp else 0, G[blk.dw[0].weight].data_ptr(),
+                            dc, B, Fi, Ti, blk.cexp, blk.k, blk.stride, st)
+            da1 = torch.empty_like(dw_in)
+            # without an expand stage the depthwise input IS the block input: fold the residual gradient in
+            L.dw_conv_dgrad(dz2.data_ptr(), R["wt"].data_ptr(), _ptr(dy) if (blk.res and not has_exp) else 0,
+                            da1.data_ptr(), dc, B, Fi, Ti, blk.cexp, blk.k, blk.stride, st)
+            if has_exp:
+                dz1 = self._bn_bwd(da1, None, None, R["z1"], R["sc1"], R["sv1"], blk.act, B, Pi, blk.cexp,
+                                   G[blk.expand[1].weight], G[blk.expand[1].bias], dev)
+                self._wgrad(dz1, R["inp"], G[blk.expand[0].weight], None, B * Pi, blk.cexp, blk.cin)
+                dinp = torch.empty_like(R["inp"])
+                self._gemm(dz1, blk.expand[0].weight, dinp, B * Pi, blk.cin, blk.cexp, w_trans=True,
+                           res=dy if blk.res else None)
+                dy = dinp
+            else:
+                dy = da1
+        # ---- stem
+        St = S["stem"]
+        conv, bn = self.stem[0], self.stem[1]
+        c0 = conv.out_channels
+        dz0 = self._bn_bwd(dy, None, None, St["z"], St["sc"], St["sv"], HS, B, St["Fo"] * St["To"], c0, G[bn.weight],
+                           G[bn.bias], dev)
+        L.stem_wgrad(dz0.data_ptr(), dc, S["x"].data_ptr(), G[conv.weight].data_ptr(), B, S["F"], S["T"], c0,
+                     conv.stride[0], st)
+        G[None] = flat
+        return G

@@ -104,11 +104,54 @@ int eat_se_fc_fwd(const float* pool, float inv_count, const float* w1, const flo
 
 /* Exact-fp32 CUDA-core GEMM: C[M,N] = epi(xf(A)[M,K] . W[N,K]^T).  1x1 convs on NHWC rows
  * (models/mn/block_types.py:140-147,167-171) and the classifier Linear layers
- * (models/mn/model.py:187-194).  gate [B,K]: SE gate of sample row/rows_per_sample. */
-int eat_gemm_simt_fwd(const void* A, int a_dtype, const float* W, void* C, int c_dtype, long long M, int N, int K,
-                      const float* in_scale, const float* in_shift, int in_act, const float* gate,
+ * (models/mn/model.py:187-194).  gate [B,K]: SE gate of sample row/rows_per_sample.
+ * w_trans = 1 reads W as [K,N] (data gradient: dA[M,Cin] = G[M,Cout] . W[Cout,Cin]). */
+int eat_gemm_simt_fwd(const void* A, int a_dtype, const float* W, int w_trans, void* C, int c_dtype, long long M,
+                      int N, int K, const float* in_scale, const float* in_shift, int in_act, const float* gate,
                       int rows_per_sample, const float* scale, const float* shift, int act, const void* residual,
                       double* stat_sum, double* stat_sq, cudaStream_t stream);
+
+/* ---- backward (training step: ex_audioset.py:197 loss.backward() over the modules above) ---- */
+
+/* Weight gradient of a 1x1 conv / Linear: dW[N,K] += G[M,N]^T . xf(A)[M,K]; db[N] += colsum(G) (db may be
+ * NULL).  dW/db are fp32 and must be zeroed by the caller once per step (atomically accumulated). */
+int eat_gemm_simt_wgrad(const void* G, int g_dtype, const void* A, int a_dtype, float* dW, float* db, long long M,
+                        int N, int K, const float* in_scale, const float* in_shift, int in_act, const float* gate,
+                        int rows_per_sample, cudaStream_t stream);
+
+/* BatchNorm backward, pass 1: s1[c] += sum dy, s2[c] += sum dy*xhat with dy = g * act'(z*scale+shift),
+ * g = gA * gate[b,c] + dpool[b,c] (gA / gate / dpool each optional).  z, gA: [B, P, C]. */
+int eat_bn_bwd_reduce(const void* gA, const float* gate, const float* dpool, const void* z, const float* scale,
+                      const float* shift, const float* mean, const float* invstd, int act, int dtype, int B, int P,
+                      int C, double* s1, double* s2, cudaStream_t stream);
+/* dgamma += s2, dbeta += s1 (either may be NULL), c1 = s1/count, c2 = s2/count. */
+int eat_bn_bwd_finalize(const double* s1, const double* s2, double count, float* dgamma, float* dbeta, float* c1,
+                        float* c2, int C, cudaStream_t stream);
+/* pass 2: dz = scale * (dy - c1 - xhat * c2). */
+int eat_bn_bwd_apply(const void* gA, const float* gate, const float* dpool, const void* z, const float* scale,
+                     const float* shift, const float* mean, const float* invstd, int act, const float* c1,
+                     const float* c2, void* dz, int dtype, int B, int P, int C, cudaStream_t stream);
+
+/* SE backward: dgate[b,c] += sum_p dp[b,p,c] * act(z[b,p,c]*scale[c]+shift[c]). */
+int eat_se_bwd_reduce(const void* dp, const void* z, const float* scale, const float* shift, int act, float* dgate,
+                      int dtype, int B, int P, int C, cudaStream_t stream);
+/* SE MLP backward (per sample): du2 = dgate*gate*(1-gate), du1 = (W2^T du2)*(hidden>0),
+ * dpool = (W1^T du1) * inv_count.  Weight gradients follow from du2/du1 via eat_gemm_simt_wgrad. */
+int eat_se_fc_bwd(const float* dgate, const float* gate, const float* hidden, const float* w1, const float* w2,
+                  float inv_count, float* du2, float* du1, float* dpool, int B, int C, int S, cudaStream_t stream);
+
+/* Depthwise conv backward: data gradient (+ optional residual add into din) and weight gradient
+ * (dw [C,1,k,k] fp32, atomically accumulated; in may carry the producing layer's BN+act as in_*). */
+int eat_dw_conv_dgrad(const void* dz, const float* wt, const void* res, void* din, int dtype, int B, int F, int T,
+                      int C, int k, int stride, cudaStream_t stream);
+int eat_dw_conv_wgrad(const void* dz, const void* in, const float* in_scale, const float* in_shift, int in_act,
+                      float* dw, int dtype, int B, int F, int T, int C, int k, int stride, cudaStream_t stream);
+/* Stem weight gradient (the spectrogram itself needs no gradient). */
+int eat_stem_wgrad(const void* dz, int dtype, const float* x, float* dw, int B, int F, int T, int C, int stride,
+                   cudaStream_t stream);
+/* dpre = dh * mask * act'(pre), fp32 vectors (classifier Hardswish + Dropout backward). */
+int eat_act_bwd(const float* dh, const float* pre, const float* mask, int act, float* dpre, long long n,
+                cudaStream_t stream);
 
 #ifdef __cplusplus
 }

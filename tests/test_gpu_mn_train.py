@@ -1,0 +1,62 @@
+"""GPU parity of the MN training step (batch-statistics forward + hand-written backward) against the
+reference's golden vectors: loss, logits, per-parameter gradient norms and samples, BatchNorm running stats.
+Tolerances (fp32 mode): logits 1e-3, loss 1e-5, gradient norms 5e-3 relative, samples 5e-3 of the tensor's
+max gradient."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import build_model, golden, net_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(tag, precision="fp32"):
+    g = golden(tag)
+    model = build_model(tag, precision=precision).cuda().train()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    model.engine().dropout_p = 0.0
+    spec, y = net_inputs(tag)
+    logits, _ = model(spec.cuda())
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, y.cuda())
+    loss.backward()
+    return g, model, logits, loss
+
+
+@pytest.mark.parametrize("tag", ["mn10", "mn04"])
+def test_mn_train_step_matches_reference_vectors(tag):
+    g, model, logits, loss = _run(tag)
+    assert np.abs(logits.detach().cpu().numpy() - g["train_logits"]).max() < 1e-3
+    assert abs(loss.item() - float(g["train_loss"])) < 1e-5
+    params = dict(model.named_parameters())
+    names = [str(n) for n in g["grad_names"]]
+    assert set(names) == set(params)
+    bad = []
+    for i, n in enumerate(names):
+        gr = params[n].grad
+        assert gr is not None, n
+        gr = gr.detach().float().cpu()
+        gn = gr.double().norm().item()
+        ref = g["grad_norm"][i]
+        idx = torch.linspace(0, gr.numel() - 1, 4).long()
+        samp = gr.flatten()[idx].numpy()
+        ok = abs(gn - ref) <= 5e-3 * ref + 1e-7 and np.abs(samp - g["grad_samples"][i]).max() <= 5e-3 * max(gr.abs().max().item(), 1e-7) + 1e-8
+        if not ok:
+            bad.append(f"{n}: norm {gn:.6e} vs {ref:.6e}; samples {samp} vs {g['grad_samples'][i]}")
+    assert not bad, "\n".join(bad[:40])
+    for i, n in enumerate(str(s) for s in g["bn_names"]):
+        bn = dict(model.named_modules())[n]
+        assert np.abs(bn.running_mean[:4].cpu().numpy() - g["bn_rm4"][i]).max() < 1e-4, n
+        assert np.abs(bn.running_var[:4].cpu().numpy() - g["bn_rv4"][i]).max() < 1e-4, n
+        assert int(bn.num_batches_tracked) == 1
+
+
+def test_mn_train_bf16_runs_and_is_close():
+    g, model, logits, loss = _run("mn10", precision="bf16")
+    assert abs(loss.item() - float(g["train_loss"])) < 5e-3
+    params = dict(model.named_parameters())
+    tot = sum(p.grad.double().pow(2).sum().item() for p in params.values()) ** 0.5
+    ref = float(np.sqrt((g["grad_norm"] ** 2).sum()))
+    assert abs(tot - ref) < 0.1 * ref
