@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Headline benchmark: clips/sec (10 s @ 32 kHz) of the mn10_as training step (mel + forward + backward +
+Adam, the body of reference ex_audioset.py:135-199) on N B200s of one node, weak scaling by clip batch.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # the reference algorithm on the host cores (oracle port, CPU)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions of every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CLIP_SAMPLES = 320000            # 10 s @ 32 kHz
+N_CLASSES = 527
+METRIC = "clips/sec (10s@32kHz) mn10_as fwd+bwd"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=128, help="clips per GPU per step")
+    ap.add_argument("--precision", default=os.environ.get("EAT_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--model", default="mn10")
+    ap.add_argument("--cpu-baseline-batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop, self.thread = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower() == "active" for r in self.rows)]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_step_factory(batch, width=1.0):
+    """The reference algorithm (oracle port: plain PyTorch ops, fp32) for one training step on the host."""
+    from oracle import mel_oracle, net_oracle
+    from efficientat_b200.models.mn.model import get_model
+    from efficientat_b200.synth import synth_labels, synth_state_, synth_waveform
+    torch.manual_seed(0)
+    model = synth_state_(get_model(width_mult=width, verbose=False), seed=7)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    names = [k for k, _ in model.named_parameters()]
+    for k in names:
+        sd[k].requires_grad_(True)
+    opt = torch.optim.Adam([sd[k] for k in names], lr=8e-4)
+    wave = synth_waveform(batch, CLIP_SAMPLES, seed=1)
+    y = synth_labels(batch, N_CLASSES, seed=2)
+
+    def step():
+        spec = mel_oracle.mel_forward(wave).unsqueeze(1)
+        logits, _ = net_oracle.mn_forward(sd, spec, width_mult=width, training=True)
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, y)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return float(loss)
+    return step
+
+
+def time_cpu_reference(batch, steps, warmup):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_reference_step_factory(batch)
+    for _ in range(max(1, warmup)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps, cores
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    k = min(args.steps, 5)
+    w = min(args.warmup, 1)
+    b = args.cpu_baseline_batch
+    value, s_per_step, cores = time_cpu_reference(b, k, w)
+    sample = f"{k} steps x {b} clips (mel+fwd+bwd+Adam, fp32, oracle port of the reference modules)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": args.gpus,
+            "steps": k, "warmup": w, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "mn10_as training step (mel+fwd+bwd+Adam) on host cores", "model": args.model,
+                       "batch_per_step": b},
+            "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def algo_bytes(name, a):
+    """Algorithmic HBM bytes of one launch from its C-ABI arguments (operands read once + result written once)."""
+    sz = lambda code: 2 if code == 1 else 4
+    if name == "eat_gemm_simt_fwd" or name == "eat_pw_tc_fwd":
+        A, adt, W, wt, C, cdt, M, N, K = a[:9]
+        res = a[17]
+        return M * K * sz(adt) + M * N * sz(cdt) * (2 if res else 1) + N * K * 4
+    if name == "eat_gemm_simt_wgrad":
+        G, gdt, A, adt, dW, db, M, N, K = a[:9]
+        return M * N * sz(gdt) + M * K * sz(adt) + N * K * 4
+    if name == "eat_dw_conv_fwd":
+        inp, wt, out, dt, B, F, T, C, k, s = a[:10]
+        Fo, To = (F + 2 * ((k - 1) // 2) - k) // s + 1, (T + 2 * ((k - 1) // 2) - k) // s + 1
+        return B * C * sz(dt) * (F * T + Fo * To)
+    if name in ("eat_bn_bwd_reduce", "eat_bn_bwd_apply"):
+        gA = a[0]
+        if name == "eat_bn_bwd_reduce":
+            dt, B, P, C = a[9:13]
+            return B * P * C * sz(dt) * (2 if gA else 1)
+        dt, B, P, C = a[12:16]
+        return B * P * C * sz(dt) * (3 if gA else 2)
+    if name == "eat_dw_conv_dgrad":
+        dz, wt, res, din, dt, B, F, T, C, k, s = a[:11]
+        Fo, To = (F + 2 * ((k - 1) // 2) - k) // s + 1, (T + 2 * ((k - 1) // 2) - k) // s + 1
+        return B * C * sz(dt) * (F * T * (2 if res else 1) + Fo * To)
+    if name == "eat_dw_conv_wgrad":
+        dz, inp, s0, s1, act, dw, dt, B, F, T, C, k, s = a[:13]
+        Fo, To = (F + 2 * ((k - 1) // 2) - k) // s + 1, (T + 2 * ((k - 1) // 2) - k) // s + 1
+        return B * C * sz(dt) * (F * T + Fo * To)
+    if name == "eat_mel_fwd":
+        B, N = a[1], a[2]
+        hop, n_mels = a[5], a[12]
+        return B * N * 4 + B * n_mels * (1 + (N - 1) // hop) * 4
+    return None
+
+
+class KernelTimer:
+    """Wraps the ctypes launchers: CUDA events around launches of the selected C-ABI entry points."""
+
+    def __init__(self, lib, only=None):
+        self.lib, self.only, self.records, self.orig = lib, only, [], {}
+
+    def __enter__(self):
+        for name in self.lib.protos:
+            short = name[4:]
+            fn = getattr(self.lib, short)
+            if self.only is not None and name not in self.only:
+                continue
+            if self.lib.protos[name][0] is not __import__("ctypes").c_int or name == "eat_abi_version":
+                continue
+            self.orig[short] = fn
+            setattr(self.lib, short, self._wrap(name, fn))
+        return self
+
+    def _wrap(self, name, fn):
+        def call(*args):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(*args)
+            e1.record()
+            self.records.append((name, e0, e1, algo_bytes(name, args)))
+        return call
+
+    def __exit__(self, *a):
+        for short, fn in self.orig.items():
+            setattr(self.lib, short, fn)
+
+    def table(self):
+        agg = {}
+        for name, e0, e1, nbytes in self.records:
+            ms = e0.elapsed_time(e1)
+            t = agg.setdefault(name, [0.0, 0, 0, True])
+            t[0] += ms
+            t[1] += 1
+            if nbytes is None:
+                t[3] = False
+            else:
+                t[2] += nbytes
+        return agg
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from efficientat_b200._lib import lib
+    from efficientat_b200.models.mn.model import get_model
+    from efficientat_b200.models.preprocess import AugmentMelSTFT
+    from efficientat_b200.synth import synth_labels, synth_state_, synth_waveform
+    from efficientat_b200.train import AudioSetTrainer
+    import contextlib, io
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = lib()
+    L.device_check(local)
+
+    B = args.batch
+    width = {"mn10": 1.0, "mn04": 0.4, "mn20": 2.0, "mn40": 4.0}[args.model]
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = synth_state_(get_model(width_mult=width, precision=args.precision, verbose=False), seed=7).to(dev)
+        mel = AugmentMelSTFT(freqm=0, timem=0).to(dev)          # ex_audioset.py defaults: freqm = timem = 0
+    trainer = AudioSetTrainer(model, mel, lr=8e-4, kd_lambda=0.1, mixup_alpha=0.3)
+    import numpy as np
+    np.random.seed(rank)
+    torch.manual_seed(100 + rank)
+
+    # synthetic shard for this rank: waveforms, labels, teacher soft targets (sigmoid of N(0,1) logits)
+    wave_h = synth_waveform(B, CLIP_SAMPLES, seed=1000 + rank).pin_memory()
+    y_h = synth_labels(B, N_CLASSES, seed=2000 + rank).pin_memory()
+    t_h = torch.sigmoid(torch.randn(B, N_CLASSES, generator=torch.Generator().manual_seed(3000 + rank))).pin_memory()
+    wave, y, teacher = wave_h.to(dev), y_h.to(dev), t_h.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also finds the dominant kernel for the roofline figure)
+    for _ in range(max(args.warmup - 1, 2)):
+        trainer.step(wave, y, teacher)
+    torch.cuda.synchronize()
+    with KernelTimer(L) as kt:
+        trainer.step(wave, y, teacher)
+        torch.cuda.synchronize()
+    prof = kt.table()
+    top = max(prof.items(), key=lambda kv: kv[1][0])[0]
+    step_launches_before = L.launches
+    trainer.step(wave, y, teacher)
+    launches_per_step = L.launches - step_launches_before
+
+    # ---- timed region: device-resident inputs
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks, KernelTimer(L, only={top}) as kt2:
+        e0.record()
+        for _ in range(args.steps):
+            loss = trainer.step(wave, y, teacher)
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * args.steps / (ms * 1e-3)
+    top_ms, top_n, top_bytes, bytes_ok = kt2.table()[top]
+
+    # ---- end to end: pinned host buffers -> H2D -> step -> D2H loss, every step
+    barrier()
+    t0 = time.perf_counter()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        w_d = wave_h.to(dev, non_blocking=True)
+        y_d = y_h.to(dev, non_blocking=True)
+        t_d = t_h.to(dev, non_blocking=True)
+        loss = trainer.step(w_d, y_d, t_d)
+        loss_host = loss.cpu()                      # device -> host read of the step's result (synchronises)
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    h2d = wave_h.numel() * 4 + y_h.numel() * 4 + t_h.numel() * 4
+    d2h = loss_host.numel() * 8
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        achieved = (top_bytes / 1e9) / (top_ms * 1e-3) if (bytes_ok and top_ms > 0) else None
+        shares = {k: round(v[0] / sum(x[0] for x in prof.values()), 4) for k, v in
+                  sorted(prof.items(), key=lambda kv: -kv[1][0])[:8]}
+        line = {
+            "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.model}_as training step: mel + mixup + fwd + BCE/KD loss + bwd + Adam "
+                                   f"(ex_audioset.py:135-199), batch {B}/GPU, 10 s @ 32 kHz clips",
+                       "model": f"{args.model}_as", "global_batch": B * world, "parallelism": f"dp{world}",
+                       "precision_mode": args.precision,
+                       "l2": "inputs (waveforms %.0f MB/GPU) exceed L2; no explicit flush" % (wave.numel() * 4 / 1e6)},
+            "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                         "launches_timed": top_n, "avg_launch_ms": top_ms / max(top_n, 1),
+                         "algorithmic_bytes_per_launch": top_bytes / max(top_n, 1) if bytes_ok else None},
+            "kernel_time_shares": shares,
+            "loss": [float(v) for v in loss_host.tolist()],
+        }
+        if not args.no_cpu_baseline and world == 1:
+            v, s_per_step, cores = time_cpu_reference(args.cpu_baseline_batch, 2, 1)
+            line["cpu_baseline"] = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
+                                    "sample": f"2 steps x {args.cpu_baseline_batch} clips, same training step, fp32, "
+                                              "oracle port of the reference modules on the host cores"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)

@@ -44,6 +44,7 @@ class _Lib:
                 f"{LIB_PATH} not found: build it with `python -m efficientat_b200.build` "
                 "(the product path has no CPU / PyTorch fallback)")
         self._dll = ctypes.CDLL(LIB_PATH)
+        self.launches = 0          # number of C-ABI kernel launchers called (bench.py: gpu_launches)
         self.protos = parse_header()
         for name, (ret, args) in self.protos.items():
             fn = getattr(self._dll, name)
@@ -59,6 +60,7 @@ class _Lib:
         last_error.restype = ctypes.c_char_p
 
         def call(*args):
+            self.launches += 1
             rc = fn(*args)
             if rc != 0:
                 raise EatError(f"{name} failed (code {rc}): {last_error().decode()}")

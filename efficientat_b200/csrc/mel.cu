@@ -10,6 +10,7 @@
 // Algorithmic HBM bytes: 4*N read + 4*n_mels*T written per clip (1.792 MB at 10 s / 32 kHz).
 #include "common.cuh"
 #include "fft_core.cuh"
+#include <math.h>
 
 namespace {
 
@@ -146,7 +147,49 @@ __global__ void mel_mask_kernel(float* __restrict__ spec, int B, int F, int T, c
   }
 }
 
+// Kaldi triangular filterbank in banded form, built on the device (training: fmin/fmax change every call,
+// reference models/preprocess.py:45-55 rebuilds it on the CPU and copies it over).  One thread per mel row;
+// same fp32 op order as torchaudio.compliance.kaldi.get_mel_banks(vtln_warp = 1).
+__global__ void mel_filterbank_kernel(int n_mels, int n_bins /* n_fft/2 */, float bin_width, float mel_lo, float delta,
+                                      int* __restrict__ fb_start, int* __restrict__ fb_len, float* __restrict__ fb_w,
+                                      int cap) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n_mels) return;
+  const float left = mel_lo + (float)m * delta;
+  const float center = mel_lo + ((float)m + 1.0f) * delta;
+  const float right = mel_lo + ((float)m + 2.0f) * delta;
+  int first = -1, last = -1;
+  for (int j = 0; j < n_bins; ++j) {
+    const float mel = 1127.0f * logf(1.0f + bin_width * (float)j / 700.0f);
+    const float w = fmaxf(0.f, fminf((mel - left) / (center - left), (right - mel) / (right - center)));
+    if (w != 0.f) { if (first < 0) first = j; last = j; }
+  }
+  int len = first < 0 ? 0 : last - first + 1;
+  if (len > cap) len = cap;
+  fb_start[m] = first < 0 ? 0 : first;
+  fb_len[m] = len;
+  for (int i = 0; i < len; ++i) {
+    const float mel = 1127.0f * logf(1.0f + bin_width * (float)(first + i) / 700.0f);
+    fb_w[(size_t)i * n_mels + m] = fmaxf(0.f, fminf((mel - left) / (center - left), (right - mel) / (right - center)));
+  }
+}
+
 }  // namespace
+
+extern "C" int eat_mel_filterbank(int n_mels, int n_fft, float sample_rate, double fmin, double fmax, int* fb_start,
+                                  int* fb_len, float* fb_w, int cap, cudaStream_t stream) {
+  const double nyq = 0.5 * sample_rate;
+  if (fmax <= 0.0) fmax += nyq;
+  if (!(0.0 <= fmin && fmin < nyq && 0.0 < fmax && fmax <= nyq && fmin < fmax) || n_mels < 1 || cap < 1) {
+    eat_set_error("eat_mel_filterbank: bad fmin/fmax"); return EAT_ERR_ARG;
+  }
+  const double mel_lo = 1127.0 * log(1.0 + fmin / 700.0), mel_hi = 1127.0 * log(1.0 + fmax / 700.0);
+  const double delta = (mel_hi - mel_lo) / (n_mels + 1);
+  mel_filterbank_kernel<<<(n_mels + 63) / 64, 64, 0, stream>>>(n_mels, n_fft / 2, sample_rate / n_fft, (float)mel_lo,
+                                                              (float)delta, fb_start, fb_len, fb_w, cap);
+  EAT_CHECK_LAUNCH();
+  return EAT_OK;
+}
 
 extern "C" int eat_mel_mask(float* spec, int B, int F, int T, const int* f_start, const int* f_end,
                             const int* t_start, const int* t_end, float fill, cudaStream_t stream) {

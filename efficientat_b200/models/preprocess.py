@@ -75,6 +75,18 @@ class AugmentMelSTFT(nn.Module):
             self._fb_cache[key] = hit
         return hit
 
+    def _device_filterbank(self, fmin, fmax, device):
+        cap = self.n_fft // 2 + 1
+        buf = getattr(self, "_fb_dev", None)
+        if buf is None or buf[0].device != device:
+            buf = (torch.empty(self.n_mels, dtype=torch.int32, device=device),
+                   torch.empty(self.n_mels, dtype=torch.int32, device=device),
+                   torch.empty(cap, self.n_mels, dtype=torch.float32, device=device))
+            self._fb_dev = buf
+        lib().mel_filterbank(self.n_mels, self.n_fft, float(self.sr), float(fmin), float(fmax), buf[0].data_ptr(),
+                             buf[1].data_ptr(), buf[2].data_ptr(), cap, torch.cuda.current_stream().cuda_stream)
+        return buf[0], buf[1], buf[2], cap
+
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError("efficientat_b200.AugmentMelSTFT runs on CUDA (sm_100a) only; got a CPU tensor")
@@ -86,7 +98,11 @@ class AugmentMelSTFT(nn.Module):
         fmax = self.fmax + self.fmax_aug_range // 2 - torch.randint(self.fmax_aug_range, (1,)).item()
         if not self.training:
             fmin, fmax = self.fmin, self.fmax
-        start, length, taps, max_len = self._filterbank(fmin, fmax, x.device)
+        if self.training and (self.fmin_aug_range > 1 or self.fmax_aug_range > 1):
+            # jittered filterbank: build it on the device, no host work or copy in the step
+            start, length, taps, max_len = self._device_filterbank(fmin, fmax, x.device)
+        else:
+            start, length, taps, max_len = self._filterbank(fmin, fmax, x.device)
         b, n = x.shape
         t = 1 + (n - 1) // self.hopsize
         out = torch.empty(b, self.n_mels, t, device=x.device, dtype=torch.float32)

@@ -55,6 +55,11 @@ int eat_mel_fwd(const float* wave, int B, int N, const float* window, int win_le
                 const float* twiddle, const int* fb_start, const int* fb_len, const float* fb_w, int max_len,
                 int n_mels, float preemph, float* out, cudaStream_t stream);
 
+/* Kaldi mel filterbank in banded form, built on the device (training-mode fmin/fmax jitter,
+ * models/preprocess.py:45-55 + torchaudio.compliance.kaldi.get_mel_banks).  fb_w holds cap x n_mels floats. */
+int eat_mel_filterbank(int n_mels, int n_fft, float sample_rate, double fmin, double fmax, int* fb_start,
+                       int* fb_len, float* fb_w, int cap, cudaStream_t stream);
+
 /* SpecAugment masking of the log-mel (training only): torchaudio Frequency/TimeMasking with
  * iid_masks=True, models/preprocess.py:31-38,61-63.  spec [B,F,T]; band [start,end) per example. */
 int eat_mel_mask(float* spec, int B, int F, int T, const int* f_start, const int* f_end, const int* t_start,
@@ -152,6 +157,21 @@ int eat_stem_wgrad(const void* dz, int dtype, const float* x, float* dw, int B, 
 /* dpre = dh * mask * act'(pre), fp32 vectors (classifier Hardswish + Dropout backward). */
 int eat_act_bwd(const float* dh, const float* pre, const float* mask, int act, float* dpre, long long n,
                 cudaStream_t stream);
+
+/* ---- training step around the network (ex_audioset.py:135-199) ---- */
+
+/* Spectrogram mixup, ex_audioset.py:145-146: out[b] = x[b]*lam[b] + x[perm[b]]*(1-lam[b]). */
+int eat_mixup(const float* x, const int* perm, const float* lam, float* out, int B, long long per_sample,
+              cudaStream_t stream);
+/* Hard-label + knowledge-distillation BCE-with-logits and its gradient, ex_audioset.py:149-189.
+ * loss_acc (fp64[2], caller-zeroed) += {kd*label_loss, (1-kd)*distillation_loss}; teacher/perm/lam optional
+ * (NULL teacher: plain BCE, weight 1).  dlogits = d(total loss)/d(logits), may be NULL. */
+int eat_bce_kd_loss(const float* logits, const float* y, const float* teacher, const int* perm, const float* lam,
+                    float kd_lambda, int B, int C, float* dlogits, double* loss_acc, cudaStream_t stream);
+/* torch.optim.Adam (adamw = 0) / AdamW (adamw = 1) on flat fp32 arenas, ex_audioset.py:86-91,198;
+ * grad_scale multiplies the gradient first (1/world_size after a sum all-reduce). step counts from 1. */
+int eat_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int adamw, int step, float grad_scale, cudaStream_t stream);
 
 #ifdef __cplusplus
 }
