@@ -47,7 +47,8 @@ class MNEngine:
         self.precision = getattr(model, "precision", "fp32")
         if self.precision not in ("fp32", "bf16"):
             raise ValueError(f"precision must be 'fp32' or 'bf16', got {self.precision}")
-        self.gemm_impl = os.environ.get("EAT_GEMM", "auto")     # auto | simt | tc
+        self.gemm_impl = os.environ.get("EAT_GEMM", "auto")     # auto | simt (exact-fp32 CUDA cores everywhere)
+        self.tc_min_rows = 1024                                  # tiny GEMMs (classifier, SE) stay on CUDA cores
         self._plan()
 
     # ------------------------------------------------------------------ structure
@@ -104,9 +105,13 @@ class MNEngine:
                 _ptr(gate), rows_per_sample, scale, shift, act, _ptr(res),
                 _ptr(stats[0]) if stats is not None else 0, _ptr(stats[1]) if stats is not None else 0, _stream())
         L = lib()
-        use_tc = self.gemm_impl == "tc" or (self.gemm_impl == "auto" and hasattr(L, "pw_tc_fwd") and
-                                            a_code == c_code and not w_trans and M >= 128 and K % 8 == 0 and N % 8 == 0)
-        if use_tc and hasattr(L, "pw_tc_fwd"):
+        use_tc = (self.gemm_impl != "simt" and a_code == c_code and M >= self.tc_min_rows and K % 8 == 0
+                  and N % 8 == 0)
+        if use_tc:
+            if w_trans:      # data gradient: feed W^T [N, K] as a K-major operand
+                wt = torch.empty(N, K, device=w.device, dtype=torch.float32)
+                L.transpose_f32(w.data_ptr(), wt.data_ptr(), K, N, _stream())
+                args = (args[0], args[1], wt.data_ptr(), 0) + args[4:]
             L.pw_tc_fwd(*args)
         else:
             L.gemm_simt_fwd(*args)

@@ -116,6 +116,16 @@ int eat_gemm_simt_fwd(const void* A, int a_dtype, const float* W, int w_trans, v
                       int rows_per_sample, const float* scale, const float* shift, int act, const void* residual,
                       double* stat_sum, double* stat_sq, cudaStream_t stream);
 
+/* tcgen05 tensor-core version of the same GEMM contract (w_trans must be 0; A and C share the dtype;
+ * K, N multiples of 8).  bf16 storage: one bf16 MMA per product; fp32 storage: hi/lo split, three MMAs
+ * (fp32-grade products, ~2^-16 relative).  Same reference call sites as eat_gemm_simt_fwd. */
+int eat_pw_tc_fwd(const void* A, int a_dtype, const float* W, int w_trans, void* C, int c_dtype, long long M, int N,
+                  int K, const float* in_scale, const float* in_shift, int in_act, const float* gate,
+                  int rows_per_sample, const float* scale, const float* shift, int act, const void* residual,
+                  double* stat_sum, double* stat_sq, cudaStream_t stream);
+/* out[cols, rows] = in[rows, cols]^T (fp32); used to feed W^T to the data-gradient GEMM. */
+int eat_transpose_f32(const float* in, float* out, int rows, int cols, cudaStream_t stream);
+
 /* ---- backward (training step: ex_audioset.py:197 loss.backward() over the modules above) ---- */
 
 /* Weight gradient of a 1x1 conv / Linear: dW[N,K] += G[M,N]^T . xf(A)[M,K]; db[N] += colsum(G) (db may be
