@@ -26,15 +26,19 @@ def _layer_report(tag, model, spec):
     return "\n".join(lines)
 
 
+@pytest.mark.parametrize("gemm", ["simt", "auto"])
 @pytest.mark.parametrize("tag", MN_TAGS)
-def test_mn_eval_fp32_matches_reference_vectors(tag):
+def test_mn_eval_fp32_matches_reference_vectors(tag, gemm):
+    """gemm = 'simt': exact fp32 CUDA-core GEMMs; 'auto': tcgen05 GEMMs (three-bf16-MMA fp32 emulation)."""
     g = golden(tag)
     model = build_model(tag).cuda().eval()
+    model.engine().gemm_impl = gemm
     spec, _ = net_inputs(tag)
     with torch.no_grad():
         logits, feat = model(spec.cuda())
     logits, feat = logits.cpu().numpy(), feat.cpu().numpy()
     err = np.abs(logits - g["eval_logits"]).max()
+    print(f"[parity] {tag} gemm={gemm}: logit max-abs err {err:.3e}")
     if not err < 1e-3:
         pytest.fail(f"logit max-abs err {err}\n" + _layer_report(tag, model, spec))
     assert np.abs(feat - g["eval_feat"]).max() < 1e-3
