@@ -3,17 +3,21 @@
 // Replaces the 1x1 ConvNormActivation layers of the reference (models/mn/block_types.py:140-147,
 // 167-171; models/mn/model.py:160-166) -- 90 % of mn10's MACs.
 //
-// Design (one persistent CTA per SM, 9 warps, warp-specialised, mbarrier pipelines):
-//   warps 0-3  producers : global -> registers -> (BatchNorm affine + activation + SE gate of the
-//                          producing layer, fused on load) -> bf16 -> 128B-swizzled K-major smem tiles.
-//                          fp32 activations/weights are split x = hi + lo (two bf16) so that three
-//                          MMAs (hi*hi + lo*hi + hi*lo) reproduce fp32 products to ~2^-16.
-//   warp  4    MMA issuer: one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N<=256,
+// Design (one persistent CTA per SM, 17 warps, warp-specialised, mbarrier pipelines):
+//   warps 0-7  producers : two groups of 4 warps that fill alternate pipeline stages, so the global-load
+//                          latency of stage s+1 overlaps the conversion of stage s.  global -> registers ->
+//                          (BatchNorm affine + activation + SE gate of the producing layer, fused on load)
+//                          -> bf16 -> 128B-swizzled K-major smem tiles.  fp32 activations/weights are split
+//                          x = hi + lo (two bf16) so that three MMAs (hi*hi + lo*hi + hi*lo) reproduce fp32
+//                          products to ~2^-16.  Only the 16-byte chunks the MMAs will read are produced.
+//   warp  8    MMA issuer: one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N<=256,
 //                          K=16) on UMMA smem descriptors; accumulators live in TMEM (2 x 256 columns,
 //                          double buffered so the epilogue of tile i overlaps the MMAs of tile i+1).
-//   warps 5-8  epilogue  : tcgen05.ld (32 lanes x 32 columns) -> BN affine / activation / residual ->
-//                          per-warp smem transpose -> 128-byte coalesced stores; per-channel batch
-//                          statistics (sum, sum of squares) accumulated in registers across tiles.
+//   warps 9-16 epilogue  : two warps per TMEM lane quadrant (even / odd 32-column chunks).  tcgen05.ld
+//                          (32 lanes x 32 columns) -> per-warp smem transpose -> 16-byte vector path:
+//                          BN affine / activation / residual (loads issued up front) -> 512-byte coalesced
+//                          stores; per-channel batch statistics (sum, sum of squares) reduced with two
+//                          shuffles per chunk and kept in shared memory across tiles.
 // The kernel is HBM-bound for mn10 widths (arithmetic intensity below the ridge); algorithmic bytes per
 // launch = M*K*sizeof(A) + M*N*sizeof(C) (+ residual) + N*K*4.
 #include "common.cuh"
@@ -22,10 +26,12 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                 // bf16 elements per k-block (= one 128-byte swizzle row)
-constexpr int kProducerThreads = 128;
-constexpr int kThreads = 288;          // 4 producer warps + 1 MMA warp + 4 epilogue warps
-constexpr int kMmaWarp = 4;
-constexpr int kFirstEpiWarp = 5;
+constexpr int kGroupThreads = 128;     // one producer group (4 warps) fills one pipeline stage
+constexpr int kThreads = 544;          // 8 producer warps + 1 MMA warp + 8 epilogue warps
+constexpr int kMmaWarp = 8;
+constexpr int kFirstEpiWarp = 9;
+constexpr int kEpiThreads = 256;
+constexpr int STG_LD = 36;             // floats per staged row: 16-byte aligned rows, conflict-free both ways
 constexpr int A_TILE_BYTES = BM * 128; // 16 KB
 
 struct TcParams {
@@ -58,11 +64,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n"
       ".reg .pred P1;\n"
       "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"     // suspends up to the time hint
       "@P1 bra DONE;\n"
       "bra LAB_WAIT;\n"
       "DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity) : "memory");
+      "}\n" ::"r"(bar), "r"(parity), "r"(0x989680) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -151,6 +157,35 @@ __device__ __forceinline__ void load_chunk<__nv_bfloat16>(const __nv_bfloat16* p
 }
 
 // ------------------------------------------------------------------------------------------ kernel
+template <typename T> struct OutVec;
+template <> struct OutVec<float> {
+  __device__ __forceinline__ static void load(const float* p, float (&v)[4]) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ __forceinline__ static void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct OutVec<__nv_bfloat16> {
+  __device__ __forceinline__ static void load(const __nv_bfloat16* p, float (&v)[4]) {
+    uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+    float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  __device__ __forceinline__ static void store(__nv_bfloat16* p, const float (&v)[4]) {
+    uint2 t;
+    t.x = pack_bf16(v[0], v[1]); t.y = pack_bf16(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = t;
+  }
+};
+
+__device__ __forceinline__ float act_sel(float v, int act) {     // branch-free activation
+  const float r = fmaxf(v, 0.f);
+  const float h = v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+  return act == EAT_ACT_HSWISH ? h : (act == EAT_ACT_RELU ? r : v);
+}
+
 // T: activation storage type.  NP = 1: operands rounded to bf16 (bf16 mode); NP = 2: hi/lo split (fp32 mode).
 template <typename T, int NP, int STAGES, int BN_MAX>
 __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
@@ -158,10 +193,11 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
   constexpr int STAGE_BYTES = NP * (A_TILE_BYTES + B_TILE_BYTES);
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* stage_base = smem;
-  float* s_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);      // 4 warps x 32 x 33 floats
-  float* s_scale = s_stage + 4 * 32 * 33;                                      // [BN_MAX]
+  float* s_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);      // 8 warps x 32 x STG_LD floats
+  float* s_scale = s_stage + 8 * 32 * STG_LD;                                  // [BN_MAX]
   float* s_shift = s_scale + BN_MAX;                                           // [BN_MAX]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + BN_MAX);              // full[S], empty[S], tfull[2], tempty[2]
+  float* s_stat = s_shift + BN_MAX;                                            // [8 warps][2][BN_MAX]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + 8 * 2 * BN_MAX);       // full[S], empty[S], tfull[2], tempty[2]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -169,14 +205,15 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
   const uint32_t bar_tfull = smem_u32(bars + 2 * STAGES), bar_tempty = smem_u32(bars + 2 * STAGES + 2);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, kProducerThreads); mbar_init(bar_empty + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 128); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, kGroupThreads); mbar_init(bar_empty + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, kEpiThreads); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
+  for (int i = threadIdx.x; i < 8 * 2 * BN_MAX; i += kThreads) s_stat[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -185,95 +222,113 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int K = p.K, N = p.N, BN = p.BN;
 
-  if (warp < 4) {
-    // ================================================================= producers
-    const int ptid = threadIdx.x;
-    const int kc = ptid & 7, r0 = ptid >> 3;        // this thread's 16-byte chunk column and first row
+  if (warp < 8) {
+    // ================================================================= producers (two groups, alternate stages)
+    const int grp = warp >> 2;
+    const int gtid = threadIdx.x & (kGroupThreads - 1);
     const T* __restrict__ A = reinterpret_cast<const T*>(p.A);
-    int stage = 0;
-    uint32_t phase = 0;
+    const int rps = p.xf.rows_per_sample;
+    int it = 0;                                                    // global (tile, k-block) counter of this CTA
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;       // m fastest: a CTA stays on one N tile
       const long long m0 = (long long)mt * BM;
       const int n0 = nt * BN;
-      const float* gate_row[8];
-      if (p.xf.gate != nullptr) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          long long m = m0 + r0 + 16 * i;
-          gate_row[i] = m < p.M ? p.xf.gate + (m / p.xf.rows_per_sample) * K : nullptr;
-        }
-      }
-      for (int kb = 0; kb < p.k_blocks; ++kb) {
+      const int b0 = p.xf.gate != nullptr ? (int)(m0 / rps) : 0;
+      const int off0 = p.xf.gate != nullptr ? (int)(m0 - (long long)b0 * rps) : 0;
+      for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
+        if ((it & 1) != grp) continue;
+        const int stage = it % STAGES;
+        const uint32_t phase = (uint32_t)(it / STAGES) & 1u;
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
         unsigned char* sA_hi = stage_base + stage * STAGE_BYTES;
         unsigned char* sA_lo = sA_hi + A_TILE_BYTES;                       // only used when NP == 2
         unsigned char* sB_hi = sA_hi + NP * A_TILE_BYTES;
         unsigned char* sB_lo = sB_hi + B_TILE_BYTES;
+        // only the 16-byte chunks the MMAs read are produced: nch = 2 per K=16 step
+        const int krem = K - kb * BK;
+        const int nch = krem >= BK ? 8 : 2 * ((krem + 15) >> 4);
+        const int lg = nch <= 2 ? 1 : (nch <= 4 ? 2 : 3);
+        const int kc = gtid & ((1 << lg) - 1), r0 = gtid >> lg, rstep = kGroupThreads >> lg;
         const int k = kb * BK + kc * 8;
-        const bool kok = k < K;
+        const bool kok = kc < nch && k < K;                                // k >= K inside nch: zero fill
+        const bool kact = kc < nch;
         float isc[8], ish[8];
         if (p.xf.scale != nullptr && kok) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) { isc[j] = __ldg(p.xf.scale + k + j); ish[j] = __ldg(p.xf.shift + k + j); }
         }
-        // ---- A: 128 rows x 8 chunks, 8 rows per thread; loads first, then transform + store
-        float av[8][8];
+        // ---- A: 128 rows, batches of 4 rows per thread: loads first, then transform + store
+        for (int rb = r0; rb < BM; rb += 4 * rstep) {
+          float av[4][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const long long m = m0 + r0 + 16 * i;
-          if (kok && m < p.M) load_chunk<T>(A + m * K + k, av[i]);
-          else {
+          for (int i = 0; i < 4; ++i) {
+            const int row = rb + i * rstep;
+            const long long m = m0 + row;
+            if (kok && row < BM && m < p.M) load_chunk<T>(A + m * K + k, av[i]);
+            else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) av[i][j] = 0.f;
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const long long m = m0 + r0 + 16 * i;
-          if (kok && m < p.M) {
-            if (p.xf.scale != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) av[i][j] = act_fwd(fmaf(av[i][j], isc[j], ish[j]), p.xf.act);
-            }
-            if (p.xf.gate != nullptr) {
-              const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate_row[i] + k));
-              const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate_row[i] + k) + 1);
-              av[i][0] *= g0.x; av[i][1] *= g0.y; av[i][2] *= g0.z; av[i][3] *= g0.w;
-              av[i][4] *= g1.x; av[i][5] *= g1.y; av[i][6] *= g1.z; av[i][7] *= g1.w;
+              for (int j = 0; j < 8; ++j) av[i][j] = 0.f;
             }
           }
-          store_chunk<NP>(sA_hi, sA_lo, swz(r0 + 16 * i, kc), av[i]);
-        }
-        // ---- B: BN rows (output channels) x 8 chunks of the fp32 weight matrix
-        for (int r = r0; r < BN; r += 16) {
-          const int n = n0 + r;
-          float wv[8];
-          if (kok && n < N) load_chunk<float>(p.W + (size_t)n * K + k, wv);
-          else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) wv[j] = 0.f;
+          for (int i = 0; i < 4; ++i) {
+            const int row = rb + i * rstep;
+            const long long m = m0 + row;
+            if (row >= BM || !kact) continue;
+            if (kok && m < p.M) {
+              if (p.xf.scale != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) av[i][j] = act_sel(fmaf(av[i][j], isc[j], ish[j]), p.xf.act);
+              }
+              if (p.xf.gate != nullptr) {
+                const int rel = off0 + row;
+                const int bb = b0 + (rps >= BM ? (rel >= rps ? 1 : 0) : rel / rps);
+                const float4* gp = reinterpret_cast<const float4*>(p.xf.gate + (size_t)bb * K + k);
+                const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
+                av[i][0] *= g0.x; av[i][1] *= g0.y; av[i][2] *= g0.z; av[i][3] *= g0.w;
+                av[i][4] *= g1.x; av[i][5] *= g1.y; av[i][6] *= g1.z; av[i][7] *= g1.w;
+              }
+            }
+            store_chunk<NP>(sA_hi, sA_lo, swz(row, kc), av[i]);
           }
-          store_chunk<NP>(sB_hi, sB_lo, swz(r, kc), wv);
+        }
+        // ---- B: BN rows (output channels) of the fp32 weight matrix, batches of 4 rows
+        for (int rb = r0; rb < BN; rb += 4 * rstep) {
+          float wv[4][8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = rb + i * rstep;
+            const int n = n0 + r;
+            if (kok && r < BN && n < N) load_chunk<float>(p.W + (size_t)n * K + k, wv[i]);
+            else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) wv[i][j] = 0.f;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = rb + i * rstep;
+            if (r < BN && kact) store_chunk<NP>(sB_hi, sB_lo, swz(r, kc), wv[i]);
+          }
         }
         fence_proxy_async();
         mbar_arrive(bar_full + 8 * stage);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == kMmaWarp) {
     // ================================================================= MMA issuer (one thread)
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(BN);
-      int stage = 0;
-      uint32_t phase = 0;
+      int it = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN_MAX;
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
+        for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
+          const int stage = it % STAGES;
+          const uint32_t phase = (uint32_t)(it / STAGES) & 1u;
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sA_hi = smem_u32(stage_base + stage * STAGE_BYTES);
@@ -292,7 +347,6 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
             }
           }
           tc_commit(bar_empty + 8 * stage);                       // frees the smem stage when these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         tc_commit(bar_tfull + 8 * acc);                           // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -300,81 +354,110 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
     }
     __syncwarp();
   } else {
-    // ================================================================= epilogue
+    // ================================================================= epilogue (2 warps per TMEM lane quadrant)
+    const int ew = warp - kFirstEpiWarp;                          // 0..7
     const int q = warp & 3;                                       // TMEM lane quadrant this warp may access
-    float* stg = s_stage + q * 32 * 33;
+    const int half = ew >> 2;                                     // even / odd 32-column chunks
+    float* stg = s_stage + ew * 32 * STG_LD;
+    float* my_sum = s_stat + ew * 2 * BN_MAX;
+    float* my_sq = my_sum + BN_MAX;
     T* __restrict__ C = reinterpret_cast<T*>(p.C);
     const T* __restrict__ R = reinterpret_cast<const T*>(p.residual);
-    const int etid = threadIdx.x - kFirstEpiWarp * 32;            // 0..127
-    constexpr int NCH = BN_MAX / 32;
-    float ssum[NCH], ssq[NCH];
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) { ssum[c] = 0.f; ssq[c] = 0.f; }
+    const int etid = threadIdx.x - kFirstEpiWarp * 32;            // 0..255
+    const int col4 = (lane & 7) * 4, rg = lane >> 3;
     int cur_nt = -1;
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool do_stats = p.stat_sum != nullptr;
-    auto flush_stats = [&](int nt) {
-      if (!do_stats || nt < 0) return;
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int n = nt * BN + c * 32 + lane;
-        if (c * 32 < BN && n < N && n < (nt + 1) * BN) {
-          atomicAdd(p.stat_sum + n, (double)ssum[c]);
-          atomicAdd(p.stat_sq + n, (double)ssq[c]);
-        }
-        ssum[c] = 0.f; ssq[c] = 0.f;
-      }
-    };
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;
       const long long m0 = (long long)mt * BM;
       const int n0 = nt * BN;
       if (nt != cur_nt) {
-        flush_stats(cur_nt);
-        cur_nt = nt;
-        // stage this N tile's epilogue affine in smem (named barrier over the 128 epilogue threads)
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int i = etid; i < BN; i += 128) {
+        // new N tile: flush the previous tile's statistics, stage this tile's epilogue affine
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int i = etid; i < BN; i += kEpiThreads) {
+          if (do_stats && cur_nt >= 0) {
+            const int n = cur_nt * BN + i;
+            float a = 0.f, b = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { a += s_stat[w * 2 * BN_MAX + i]; b += s_stat[w * 2 * BN_MAX + BN_MAX + i]; }
+            if (n < N) { atomicAdd(p.stat_sum + n, (double)a); atomicAdd(p.stat_sq + n, (double)b); }
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { s_stat[w * 2 * BN_MAX + i] = 0.f; s_stat[w * 2 * BN_MAX + BN_MAX + i] = 0.f; }
+          }
           const int n = n0 + i;
           s_scale[i] = (p.scale != nullptr && n < N) ? p.scale[n] : 1.f;
           s_shift[i] = (p.shift != nullptr && n < N) ? p.shift[n] : 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        cur_nt = nt;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN_MAX;
       const long long mrow0 = m0 + q * 32;
 #pragma unroll 1
-      for (int c = 0; c * 32 < BN; ++c) {
+      for (int c = half; c * 32 < BN; c += 2) {
         uint32_t raw[32];
         tc_ld32(trow + c * 32, raw);
-        // lane == row (mrow0 + lane), raw[j] == column n0 + c*32 + j
+        // lane == row (mrow0 + lane), raw[j] == column n0 + c*32 + j : stage row-wise with 16-byte stores
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(raw[j]);
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * j) =
+              make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                          __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
         __syncwarp();
-        const int n = n0 + c * 32 + lane;                          // now lane == column
-        const bool nok = (c * 32 + lane < BN) && n < N;
-        const float sc = s_scale[c * 32 + lane], sh = s_shift[c * 32 + lane];
-        float cs = 0.f, cq = 0.f;
-#pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-          const long long m = mrow0 + r;
-          if (m >= p.M) break;
-          float v = stg[r * 33 + lane];
-          cs += v;
-          cq = fmaf(v, v, cq);
-          if (nok) {
-            v = act_fwd(fmaf(v, sc, sh), p.act);
-            if (R != nullptr) v += to_f32<T>(R[m * N + n]);
-            C[m * N + n] = from_f32<T>(v);
+        // now lane -> (row group rg = lane / 8, 4 columns at col4); 8 iterations cover the 32 rows
+        const int cl = c * 32 + col4;
+        const int n = n0 + cl;
+        const bool nok = cl < BN && n < N;
+        const float4 sc4 = *reinterpret_cast<const float4*>(s_scale + (cl < BN_MAX ? cl : 0));
+        const float4 sh4 = *reinterpret_cast<const float4*>(s_shift + (cl < BN_MAX ? cl : 0));
+        float res[8][4];
+        if (R != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const long long m = mrow0 + i * 4 + rg;
+            if (nok && m < p.M) OutVec<T>::load(R + m * N + n, res[i]);
+            else { res[i][0] = res[i][1] = res[i][2] = res[i][3] = 0.f; }
+          }
+        }
+        float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 4 + rg;
+          const long long m = mrow0 + row;
+          const float4 v4 = *reinterpret_cast<const float4*>(stg + row * STG_LD + col4);
+          float v[4] = {v4.x, v4.y, v4.z, v4.w};
+          if (m < p.M) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { cs[j] += v[j]; cq[j] = fmaf(v[j], v[j], cq[j]); }
+            if (nok) {
+              v[0] = act_sel(fmaf(v[0], sc4.x, sh4.x), p.act);
+              v[1] = act_sel(fmaf(v[1], sc4.y, sh4.y), p.act);
+              v[2] = act_sel(fmaf(v[2], sc4.z, sh4.z), p.act);
+              v[3] = act_sel(fmaf(v[3], sc4.w, sh4.w), p.act);
+              if (R != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] += res[i][j];
+              }
+              OutVec<T>::store(C + m * N + n, v);
+            }
           }
         }
         if (do_stats) {
 #pragma unroll
-          for (int cc = 0; cc < NCH; ++cc)
-            if (cc == c) { ssum[cc] += cs; ssq[cc] += cq; }
+          for (int j = 0; j < 4; ++j) {
+            cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 8);
+            cq[j] += __shfl_xor_sync(0xffffffffu, cq[j], 8);
+            cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
+            cq[j] += __shfl_xor_sync(0xffffffffu, cq[j], 16);
+          }
+          if (lane < 8 && cl < BN) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { my_sum[cl + j] += cs[j]; my_sq[cl + j] += cq[j]; }
+          }
         }
         __syncwarp();
       }
@@ -382,7 +465,17 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
       mbar_arrive(bar_tempty + 8 * acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    flush_stats(cur_nt);
+    // final statistics flush
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (do_stats && cur_nt >= 0) {
+      for (int i = etid; i < BN; i += kEpiThreads) {
+        const int n = cur_nt * BN + i;
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { a += s_stat[w * 2 * BN_MAX + i]; b += s_stat[w * 2 * BN_MAX + BN_MAX + i]; }
+        if (n < N) { atomicAdd(p.stat_sum + n, (double)a); atomicAdd(p.stat_sq + n, (double)b); }
+      }
+    }
   }
 
   tc_fence_before();
@@ -401,8 +494,10 @@ int launch_tc(const TcParams& p0, cudaStream_t st) {
   p.n_tiles = ceil_div(p.N, p.BN);
   p.m_tiles = ceil_div(p.M, BM);
   p.k_blocks = ceil_div(p.K, BK);
-  constexpr size_t smem = (size_t)STAGES * NP * (A_TILE_BYTES + BN_MAX * 128) + 4 * 32 * 33 * sizeof(float) +
-                          2 * BN_MAX * sizeof(float) + (2 * STAGES + 4) * sizeof(uint64_t) + 16;
+  constexpr size_t smem = (size_t)STAGES * NP * (A_TILE_BYTES + BN_MAX * 128) + 8 * 32 * STG_LD * sizeof(float) +
+                          2 * BN_MAX * sizeof(float) + 16 * BN_MAX * sizeof(float) +
+                          (2 * STAGES + 4) * sizeof(uint64_t) + 16;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(pw_tc_kernel<T, NP, STAGES, BN_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -435,8 +530,8 @@ extern "C" int eat_pw_tc_fwd(const void* A, int a_dtype, const float* W, int w_t
   p.A = A; p.W = W; p.C = C; p.residual = residual; p.M = (int)M; p.N = N; p.K = K;
   p.xf = InXform{in_scale, in_shift, gate, in_act, rows_per_sample > 0 ? rows_per_sample : 1};
   p.scale = scale; p.shift = shift; p.act = act; p.stat_sum = stat_sum; p.stat_sq = stat_sq;
-  if (a_dtype == EAT_BF16) return launch_tc<__nv_bfloat16, 1, 4, 256>(p, st);
-  return launch_tc<float, 2, 3, 128>(p, st);
+  if (a_dtype == EAT_BF16) return launch_tc<__nv_bfloat16, 1, 3, 256>(p, st);
+  return launch_tc<float, 2, 2, 128>(p, st);
 }
 
 // [R, Cc] fp32 -> [Cc, R]  (weights for the data-gradient GEMM)
