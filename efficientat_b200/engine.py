@@ -347,9 +347,15 @@ class MNEngine:
                a_code=None):
         g_code = self.dcode if g_code is None else g_code
         a_code = self.dcode if a_code is None else a_code
-        lib().gemm_simt_wgrad(g.data_ptr(), g_code, a.data_ptr(), a_code, dW.data_ptr(), _ptr(db), M, N, K,
-                              _ptr(in_sc[0]) if in_sc is not None else 0, _ptr(in_sc[1]) if in_sc is not None else 0,
-                              in_act, _ptr(gate), rows_per_sample, _stream())
+        args = (g.data_ptr(), g_code, a.data_ptr(), a_code, dW.data_ptr(), _ptr(db), M, N, K,
+                _ptr(in_sc[0]) if in_sc is not None else 0, _ptr(in_sc[1]) if in_sc is not None else 0,
+                in_act, _ptr(gate), rows_per_sample, _stream())
+        use_tc = (self.gemm_impl != "simt" and db is None and g_code == a_code and M >= self.tc_min_rows
+                  and K % 8 == 0 and N % 8 == 0)
+        if use_tc:
+            lib().pw_tc_wgrad(*args)
+        else:
+            lib().gemm_simt_wgrad(*args)
 
     def _bn_bwd(self, gA, gate, dpool, z, sc, sv, act, B, P, C, dgamma, dbeta, dev):
         """two-pass BatchNorm(+activation) backward -> dz (same dtype/shape as z)."""

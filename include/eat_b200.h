@@ -134,6 +134,12 @@ int eat_gemm_simt_wgrad(const void* G, int g_dtype, const void* A, int a_dtype, 
                         int N, int K, const float* in_scale, const float* in_shift, int in_act, const float* gate,
                         int rows_per_sample, cudaStream_t stream);
 
+/* tcgen05 version of the weight gradient (db must be NULL; G and A share the dtype; K, N multiples of 8):
+ * MN-major UMMA operands, reduction over pixels split across CTAs, vector atomics into dW. */
+int eat_pw_tc_wgrad(const void* G, int g_dtype, const void* A, int a_dtype, float* dW, float* db, long long M, int N,
+                    int K, const float* in_scale, const float* in_shift, int in_act, const float* gate,
+                    int rows_per_sample, cudaStream_t stream);
+
 /* BatchNorm backward, pass 1: s1[c] += sum dy, s2[c] += sum dy*xhat with dy = g * act'(z*scale+shift),
  * g = gA * gate[b,c] + dpool[b,c] (gA / gate / dpool each optional).  z, gA: [B, P, C]. */
 int eat_bn_bwd_reduce(const void* gA, const float* gate, const float* dpool, const void* z, const float* scale,

@@ -115,3 +115,41 @@ def test_wgrad_and_transposed_gemm_match_torch():
         L.gemm_simt_fwd(G.data_ptr(), 0, W.data_ptr(), 1, dA.data_ptr(), 0, M, K, N, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, st)
         ref = G.double() @ W.double()
         assert ((dA.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_tc_wgrad_matches_torch(dtype):
+    """tcgen05 weight gradient (MN-major operands) vs float64 torch; fused input transform + SE gate included."""
+    L = lib()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    st = torch.cuda.current_stream().cuda_stream
+    code = 0 if dtype == torch.float32 else 1
+    cases = [(4096, 64, 16, 0), (5000, 72, 24, 1), (3000, 24, 72, 2), (2048, 240, 40, 0), (1100, 112, 672, 3),
+             (1024, 960, 160, 0), (700, 160, 960, 1), (40000, 16, 16, 2), (2000, 200, 80, 0), (1500, 8, 8, 0)]
+    for (M, N, K, variant) in cases:
+        G = (torch.randn(M, N, device="cuda", generator=g) * 0.1).to(dtype)
+        A = torch.randn(M, K, device="cuda", generator=g).to(dtype)
+        in_sc = gate = None
+        in_act, rps = 0, 1
+        if variant in (1, 3):
+            in_sc = torch.stack([torch.rand(K, device="cuda", generator=g) + 0.5, torch.randn(K, device="cuda", generator=g) * 0.1])
+            in_act = 2 if variant == 1 else 1
+        if variant in (2, 3):
+            rps = 53
+            gate = torch.rand((M + rps - 1) // rps, K, device="cuda", generator=g)
+        dW = torch.zeros(N, K, device="cuda")
+        p = lambda t: 0 if t is None else t.data_ptr()
+        L.pw_tc_wgrad(G.data_ptr(), code, A.data_ptr(), code, dW.data_ptr(), 0, M, N, K,
+                      p(in_sc[0]) if in_sc is not None else 0, p(in_sc[1]) if in_sc is not None else 0, in_act, p(gate),
+                      rps, st)
+        torch.cuda.synchronize()
+        a = A.double()
+        if in_sc is not None:
+            a = a * in_sc[0].double() + in_sc[1].double()
+            a = torch.relu(a) if in_act == 1 else torch.nn.functional.hardswish(a)
+        if gate is not None:
+            a = a * gate.double().repeat_interleave(rps, 0)[:M]
+        ref = G.double().t() @ a
+        err = ((dW.double() - ref).abs().max() / (ref.abs().max() + 1e-9)).item()
+        tol = 2e-4 if dtype == torch.float32 else 2e-2
+        assert err < tol, f"wgrad {dtype} {(M, N, K)} variant {variant}: rel err {err}"
