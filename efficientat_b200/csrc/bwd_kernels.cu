@@ -238,7 +238,9 @@ __global__ void __launch_bounds__(kThreads) dw_dgrad_kernel(const T* __restrict_
 }
 
 // wgrad: dw[c, ky, kx] += sum_{b, fo, to} dz[b,fo,to,c] * xf(in)[b, fo*S-PAD+ky, to*S-PAD+kx, c]
-// thread = (pixel slot, channel vector), K*K*V register accumulators, shared + global atomics at the end.
+// thread = (strip of P output columns, channel vector).  One kernel row ky at a time keeps the accumulators at
+// K*V registers; within a row the strip's input span ((P-1)*S + K vectors) is loaded and transformed once and
+// reused by all K taps.  Block partials are combined in shared memory, then one global atomic per (tap, channel).
 template <typename T, int K, int S>
 __global__ void __launch_bounds__(kThreads) dw_wgrad_kernel(const T* __restrict__ dz, const T* __restrict__ in,
                                                             InXform xf, float* __restrict__ dw /*[C,1,K,K]*/,
@@ -246,6 +248,8 @@ __global__ void __launch_bounds__(kThreads) dw_wgrad_kernel(const T* __restrict_
   constexpr int V = Vec<T>::N;
   constexpr int PAD = (K - 1) / 2;
   constexpr int KK = K * K;
+  constexpr int P = 8;
+  constexpr int NIN = (P - 1) * S + K;
   extern __shared__ float smem[];   // [KK][C]
   for (int i = threadIdx.x; i < KK * C; i += kThreads) smem[i] = 0.f;
   __syncthreads();
@@ -256,7 +260,8 @@ __global__ void __launch_bounds__(kThreads) dw_wgrad_kernel(const T* __restrict_
   const int b = blockIdx.y;
   const T* inb = in + (size_t)b * F * Tn * C;
   const T* dzb = dz + (size_t)b * Fo * To * C;
-  const int npix = Fo * To;
+  const int strips = ceil_div(To, P);
+  const int units = Fo * strips;
   if (slot < ppb) {
     for (int cvi = threadIdx.x % tcv; cvi < cv; cvi += tcv) {
       const int c0 = cvi * V;
@@ -265,31 +270,45 @@ __global__ void __launch_bounds__(kThreads) dw_wgrad_kernel(const T* __restrict_
 #pragma unroll
         for (int k = 0; k < V; ++k) { isc[k] = xf.scale[c0 + k]; ish[k] = xf.shift[c0 + k]; }
       }
-      // one kernel row at a time keeps the accumulators at K*V registers (25*8 would spill)
       for (int ky = 0; ky < K; ++ky) {
         float acc[K][V];
 #pragma unroll
         for (int q = 0; q < K; ++q)
 #pragma unroll
           for (int k = 0; k < V; ++k) acc[q][k] = 0.f;
-        for (int p = blockIdx.x * ppb + slot; p < npix; p += gridDim.x * ppb) {
-          const int fo = p / To, to = p - fo * To;
+        for (int u = blockIdx.x * ppb + slot; u < units; u += gridDim.x * ppb) {
+          const int fo = u / strips;
+          const int to0 = (u - fo * strips) * P;
           const int f = fo * S - PAD + ky;
           if (f < 0 || f >= F) continue;
-          float g[V];
-          Vec<T>::load(dzb + (size_t)p * C + c0, g);
+          float g[P][V];
 #pragma unroll
-          for (int kx = 0; kx < K; ++kx) {
-            const int t = to * S - PAD + kx;
+          for (int pp = 0; pp < P; ++pp) {
+            if (to0 + pp < To) Vec<T>::load(dzb + ((size_t)fo * To + to0 + pp) * C + c0, g[pp]);
+            else {
+#pragma unroll
+              for (int k = 0; k < V; ++k) g[pp][k] = 0.f;
+            }
+          }
+          const T* rowp = inb + (size_t)f * Tn * C + c0;
+#pragma unroll
+          for (int ix = 0; ix < NIN; ++ix) {
+            const int t = to0 * S - PAD + ix;
             if (t < 0 || t >= Tn) continue;
             float v[V];
-            Vec<T>::load(inb + ((size_t)f * Tn + t) * C + c0, v);
+            Vec<T>::load(rowp + (size_t)t * C, v);
             if (xf.scale != nullptr) {
 #pragma unroll
               for (int k = 0; k < V; ++k) v[k] = act_fwd(fmaf(v[k], isc[k], ish[k]), xf.act);
             }
 #pragma unroll
-            for (int k = 0; k < V; ++k) acc[kx][k] = fmaf(g[k], v[k], acc[kx][k]);
+            for (int pp = 0; pp < P; ++pp) {
+              const int kx = ix - pp * S;
+              if (kx >= 0 && kx < K) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) acc[kx][k] = fmaf(g[pp][k], v[k], acc[kx][k]);
+              }
+            }
           }
         }
 #pragma unroll
@@ -399,7 +418,7 @@ int launch_dw_bwd(int which, const void* dz, const float* wt, const void* in, In
 #undef EAT_DG
   } else {
     const int tcv = cv < kThreads ? cv : kThreads, ppb = kThreads / tcv;
-    dim3 grid(grid2(Fo * To, ppb, B), B);
+    dim3 grid(grid2(Fo * ceil_div(To, 8), ppb, B), B);
     size_t smem = (size_t)k * k * C * sizeof(float);
     if (smem > 200 * 1024) { eat_set_error("dw wgrad: channel count too large for the shared accumulator"); return EAT_ERR_UNSUPPORTED; }
 #define EAT_WG(KK, SS)                                                                                         \
@@ -478,9 +497,13 @@ int eat_se_fc_bwd(const float* dgate, const float* gate, const float* hidden, co
   return EAT_OK;
 }
 
+extern "C" int eat_dw_conv_dgrad_s1(const void* dz, const float* wt, const void* res, void* din, int dtype, int B,
+                                    int F, int T, int C, int k, cudaStream_t st);
+
 int eat_dw_conv_dgrad(const void* dz, const float* wt, const void* res, void* din, int dtype, int B, int F, int T,
                       int C, int k, int stride, cudaStream_t st) {
   if (B == 0) return EAT_OK;
+  if (stride == 1 && (k == 3 || k == 5)) return eat_dw_conv_dgrad_s1(dz, wt, res, din, dtype, B, F, T, C, k, st);
   InXform xf{nullptr, nullptr, nullptr, 0, 0};
   if (dtype == EAT_BF16) return launch_dw_bwd<__nv_bfloat16>(0, dz, wt, nullptr, xf, res, din, nullptr, B, F, T, C, k, stride, st);
   return launch_dw_bwd<float>(0, dz, wt, nullptr, xf, res, din, nullptr, B, F, T, C, k, stride, st);

@@ -92,16 +92,18 @@ __global__ void __launch_bounds__(kThreads) stem_kernel(
 
 // ------------------------------------------------------------------------------------------
 // Depthwise k x k conv, pad (k-1)/2, stride S.  in [B, F, T, C] -> out [B, Fo, To, C].
-// wt: repacked weights [k*k][C].  Each thread: one channel vector, a strip of P output columns.
+// wt: repacked weights [k*k][C] (flip != 0 reads them mirrored: the stride-1 data gradient is the same
+// convolution with the kernel flipped).  Each thread: one channel vector, a strip of P output columns whose
+// input span ((P-1)*S + K vectors per kernel row) is loaded/transformed once and reused by all taps.
 // grid = (chunks, B) so per-(sample, channel) pooling stays inside a CTA column.
 template <typename T, int K, int S>
-__global__ void __launch_bounds__(kThreads) dw_kernel(
+__global__ void __launch_bounds__(kThreads, 2) dw_kernel(
     const T* __restrict__ in, const float* __restrict__ wt, T* __restrict__ out,
     int F, int Tn, int Fo, int To, int C, InXform xf,
-    const float* __restrict__ scale, const float* __restrict__ shift, int act,
+    const float* __restrict__ scale, const float* __restrict__ shift, int act, const T* __restrict__ res, int flip,
     float* __restrict__ pool /*[B,C] or null*/, double* __restrict__ stat_sum, double* __restrict__ stat_sq) {
   constexpr int V = Vec<T>::N;
-  constexpr int P = 4;
+  constexpr int P = (S == 1 && V == 4) ? 8 : 4;
   constexpr int NIN = (P - 1) * S + K;
   constexpr int PAD = (K - 1) / 2;
   extern __shared__ float smem[];
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(kThreads) dw_kernel(
   for (int i = 0; i < V; ++i) { lsum[i] = 0.f; lsq[i] = 0.f; }
   const T* inb = in + (size_t)b * F * Tn * C;
   T* outb = out + (size_t)b * Fo * To * C;
+  const T* resb = res != nullptr ? res + (size_t)b * Fo * To * C : nullptr;
   // channel vectors beyond kThreads are covered by looping cvi
   for (int cvi = threadIdx.x % (cv < kThreads ? cv : kThreads); cvi < cv; cvi += kThreads) {
     const int slot = cv < kThreads ? threadIdx.x / cv : 0;
@@ -131,11 +134,6 @@ __global__ void __launch_bounds__(kThreads) dw_kernel(
     if (xf.scale != nullptr) {
 #pragma unroll
       for (int i = 0; i < V; ++i) { isc[i] = xf.scale[c0 + i]; ish[i] = xf.shift[c0 + i]; }
-    }
-    float osc[V], osh[V];
-    if (scale != nullptr) {
-#pragma unroll
-      for (int i = 0; i < V; ++i) { osc[i] = scale[c0 + i]; osh[i] = shift[c0 + i]; }
     }
     for (int u = blockIdx.x * ppb + slot; u < units; u += gridDim.x * ppb) {
       const int fo = u / strips;
@@ -153,7 +151,8 @@ __global__ void __launch_bounds__(kThreads) dw_kernel(
         float wreg[K][V];
 #pragma unroll
         for (int kx = 0; kx < K; ++kx) {
-          float4 const* wp = reinterpret_cast<float4 const*>(wt + (size_t)(ky * K + kx) * C + c0);
+          const int tap = flip ? (K * K - 1 - (ky * K + kx)) : (ky * K + kx);
+          float4 const* wp = reinterpret_cast<float4 const*>(wt + (size_t)tap * C + c0);
 #pragma unroll
           for (int q = 0; q < V / 4; ++q) {
             float4 t4 = __ldg(wp + q);
@@ -187,12 +186,19 @@ __global__ void __launch_bounds__(kThreads) dw_kernel(
         float o[V];
         if (scale != nullptr) {
 #pragma unroll
-          for (int i = 0; i < V; ++i) { o[i] = act_fwd(fmaf(acc[p][i], osc[i], osh[i]), act); lsum[i] += o[i]; }
+          for (int i = 0; i < V; ++i) { o[i] = act_fwd(fmaf(acc[p][i], scale[c0 + i], shift[c0 + i]), act); lsum[i] += o[i]; }
         } else {
 #pragma unroll
           for (int i = 0; i < V; ++i) { o[i] = acc[p][i]; lsum[i] += o[i]; lsq[i] = fmaf(o[i], o[i], lsq[i]); }
         }
-        Vec<T>::store(outb + ((size_t)fo * To + to) * C + c0, o);
+        const size_t off = ((size_t)fo * To + to) * C + c0;
+        if (resb != nullptr) {
+          float r[V];
+          Vec<T>::load(resb + off, r);
+#pragma unroll
+          for (int i = 0; i < V; ++i) o[i] += r[i];
+        }
+        Vec<T>::store(outb + off, o);
       }
     }
     if (need_red) {
@@ -371,21 +377,21 @@ inline int grid_for(long long items, int per_block, int max_blocks = 148 * 16) {
 
 template <typename T>
 int launch_dw(const T* in, const float* wt, T* out, int B, int F, int Tn, int C, int k, int stride, InXform xf,
-              const float* scale, const float* shift, int act, float* pool, double* ssum, double* ssq,
-              cudaStream_t st) {
+              const float* scale, const float* shift, int act, const T* res, int flip, float* pool, double* ssum,
+              double* ssq, cudaStream_t st) {
   constexpr int V = Vec<T>::N;
   if (C % V != 0) { eat_set_error("dw conv: channels must be a multiple of the vector width"); return EAT_ERR_ARG; }
   const int pad = (k - 1) / 2;
   const int Fo = (F + 2 * pad - k) / stride + 1, To = (Tn + 2 * pad - k) / stride + 1;
   const int cv = C / V;
   const int ppb = kThreads / cv > 0 ? kThreads / cv : 1;
-  const int units = Fo * ceil_div(To, 4);
+  const int units = Fo * ceil_div(To, (stride == 1 && V == 4) ? 8 : 4);
   int gx = ceil_div(units, ppb);
   const int cap = max(1, (148 * 8) / max(B, 1));
   if (gx > cap) gx = cap;   // grid-stride over strips; keeps per-CTA reductions coarse
   dim3 grid(gx, B);
   size_t smem = 2 * (size_t)C * sizeof(float);
-#define EAT_DW(KK, SS) dw_kernel<T, KK, SS><<<grid, kThreads, smem, st>>>(in, wt, out, F, Tn, Fo, To, C, xf, scale, shift, act, pool, ssum, ssq)
+#define EAT_DW(KK, SS) dw_kernel<T, KK, SS><<<grid, kThreads, smem, st>>>(in, wt, out, F, Tn, Fo, To, C, xf, scale, shift, act, res, flip, pool, ssum, ssq)
   if (k == 3 && stride == 1) EAT_DW(3, 1);
   else if (k == 3 && stride == 2) EAT_DW(3, 2);
   else if (k == 5 && stride == 1) EAT_DW(5, 1);
@@ -433,8 +439,18 @@ int eat_dw_conv_fwd(const void* in, const float* wt, void* out, int dtype, int B
   if (B == 0) return EAT_OK;
   InXform xf{in_scale, in_shift, nullptr, in_act, 0};
   if (dtype == EAT_BF16)
-    return launch_dw<__nv_bfloat16>((const __nv_bfloat16*)in, wt, (__nv_bfloat16*)out, B, F, T, C, k, stride, xf, scale, shift, act, pool, stat_sum, stat_sq, st);
-  return launch_dw<float>((const float*)in, wt, (float*)out, B, F, T, C, k, stride, xf, scale, shift, act, pool, stat_sum, stat_sq, st);
+    return launch_dw<__nv_bfloat16>((const __nv_bfloat16*)in, wt, (__nv_bfloat16*)out, B, F, T, C, k, stride, xf, scale, shift, act, nullptr, 0, pool, stat_sum, stat_sq, st);
+  return launch_dw<float>((const float*)in, wt, (float*)out, B, F, T, C, k, stride, xf, scale, shift, act, nullptr, 0, pool, stat_sum, stat_sq, st);
+}
+
+// stride-1 depthwise data gradient = the forward kernel with mirrored taps (+ residual-gradient add)
+int eat_dw_conv_dgrad_s1(const void* dz, const float* wt, const void* res, void* din, int dtype, int B, int F, int T,
+                         int C, int k, cudaStream_t st) {
+  if (B == 0) return EAT_OK;
+  InXform xf{nullptr, nullptr, nullptr, 0, 0};
+  if (dtype == EAT_BF16)
+    return launch_dw<__nv_bfloat16>((const __nv_bfloat16*)dz, wt, (__nv_bfloat16*)din, B, F, T, C, k, 1, xf, nullptr, nullptr, 0, (const __nv_bfloat16*)res, 1, nullptr, nullptr, nullptr, st);
+  return launch_dw<float>((const float*)dz, wt, (float*)din, B, F, T, C, k, 1, xf, nullptr, nullptr, 0, (const float*)res, 1, nullptr, nullptr, nullptr, st);
 }
 
 int eat_bn_fold(const float* gamma, const float* beta, const float* rmean, const float* rvar, float eps,

@@ -165,6 +165,8 @@ int eat_se_fc_bwd(const float* dgate, const float* gate, const float* hidden, co
  * (dw [C,1,k,k] fp32, atomically accumulated; in may carry the producing layer's BN+act as in_*). */
 int eat_dw_conv_dgrad(const void* dz, const float* wt, const void* res, void* din, int dtype, int B, int F, int T,
                       int C, int k, int stride, cudaStream_t stream);
+int eat_dw_conv_dgrad_s1(const void* dz, const float* wt, const void* res, void* din, int dtype, int B, int F, int T,
+                         int C, int k, cudaStream_t stream);   /* stride-1 fast path used by eat_dw_conv_dgrad */
 int eat_dw_conv_wgrad(const void* dz, const void* in, const float* in_scale, const float* in_shift, int in_act,
                       float* dw, int dtype, int B, int F, int T, int C, int k, int stride, cudaStream_t stream);
 /* Stem weight gradient (the spectrogram itself needs no gradient). */
