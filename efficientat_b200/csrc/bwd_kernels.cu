@@ -325,6 +325,144 @@ __global__ void __launch_bounds__(kThreads) dw_wgrad_kernel(const T* __restrict_
   }
 }
 
+// Shared-memory tiled depthwise weight gradient (same contract as dw_wgrad_kernel).  A CTA stages the transformed
+// input tile and the dz tile of one sample / 32-channel chunk in shared memory (BatchNorm+activation applied once
+// per input element), keeps all K*K tap accumulators of its channel slice in registers across its tiles, and
+// reduces them once at the end (shared atomics, then one global atomic per tap and channel).
+template <typename T, int K, int S>
+__global__ void __launch_bounds__(kThreads) dw_wgrad_tile_kernel(const T* __restrict__ dz, const T* __restrict__ in,
+                                                                 InXform xf, float* __restrict__ dw, int F, int Tn,
+                                                                 int Fo, int To, int C, long long dw_bstride) {
+  constexpr int VG = Vec<T>::N;
+  constexpr int CC = 32;
+  constexpr int VW = (K == 3) ? 4 : 2;           // channels per thread (register budget: K*K*VW accumulators)
+  constexpr int CCW = CC / VW;
+  constexpr int FR = (S == 1) ? 8 : 4;
+  constexpr int TT = (S == 1) ? 32 : 16;
+  constexpr int P = 4;
+  constexpr int SPR = TT / P;
+  constexpr int IR = (FR - 1) * S + K, IT = (TT - 1) * S + K;
+  constexpr int NIN = (P - 1) * S + K;
+  constexpr int PAD = (K - 1) / 2;
+  constexpr int KK = K * K;
+  constexpr int STRIPS = FR * SPR;
+  constexpr int PARTS = kThreads / CCW;
+  extern __shared__ __align__(16) float smem[];
+  float* s_in = smem;                            // [IR*IT][CC]
+  float* s_g = s_in + IR * IT * CC;              // [FR*TT][CC]
+  float* s_acc = s_g + FR * TT * CC;             // [KK][CC]
+  const int b = blockIdx.y;
+  const int tiles_t = ceil_div(To, TT), tiles_f = ceil_div(Fo, FR), chunks = ceil_div(C, CC);
+  const int tiles_per_chunk = tiles_t * tiles_f;
+  const int groups = gridDim.x / chunks;
+  const int chunk = blockIdx.x / groups, grp = blockIdx.x - chunk * groups;
+  if (chunk >= chunks) return;
+  const int cbase = chunk * CC;
+  const int tid = threadIdx.x;
+  const T* inb = in + (size_t)b * F * Tn * C;
+  const T* dzb = dz + (size_t)b * Fo * To * C;
+  for (int i = tid; i < KK * CC; i += kThreads) s_acc[i] = 0.f;
+  constexpr int VPP = CC / VG;
+  const int lv = tid % VPP;
+  const int lc0 = cbase + lv * VG;
+  const bool lvalid = lc0 < C;
+  float isc[VG], ish[VG];
+  if (xf.scale != nullptr && lvalid) {
+#pragma unroll
+    for (int i = 0; i < VG; ++i) { isc[i] = xf.scale[lc0 + i]; ish[i] = xf.shift[lc0 + i]; }
+  }
+  const int cw = tid % CCW, part = tid / CCW;
+  const bool cvalid = cbase + cw * VW < C;
+  float acc[KK][VW];
+#pragma unroll
+  for (int q = 0; q < KK; ++q)
+#pragma unroll
+    for (int i = 0; i < VW; ++i) acc[q][i] = 0.f;
+  for (int tile = grp; tile < tiles_per_chunk; tile += groups) {
+    const int tf = tile / tiles_t, tt = tile - tf * tiles_t;
+    const int f0 = tf * FR, t0 = tt * TT;
+    __syncthreads();
+    for (int idx = tid; idx < IR * IT * VPP; idx += kThreads) {
+      const int pix = idx / VPP;
+      const int ir = pix / IT, it = pix - ir * IT;
+      const int f = f0 * S - PAD + ir, t = t0 * S - PAD + it;
+      float v[VG];
+      if (lvalid && f >= 0 && f < F && t >= 0 && t < Tn) {
+        Vec<T>::load(inb + ((size_t)f * Tn + t) * C + lc0, v);
+        if (xf.scale != nullptr) {
+#pragma unroll
+          for (int i = 0; i < VG; ++i) v[i] = act_fwd(fmaf(v[i], isc[i], ish[i]), xf.act);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < VG; ++i) v[i] = 0.f;
+      }
+      float* dst = s_in + (size_t)pix * CC + lv * VG;
+#pragma unroll
+      for (int q = 0; q < VG / 4; ++q)
+        *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+    for (int idx = tid; idx < FR * TT * VPP; idx += kThreads) {
+      const int pix = idx / VPP;
+      const int fl = pix / TT, tl = pix - fl * TT;
+      const int fo = f0 + fl, to = t0 + tl;
+      float v[VG];
+      if (lvalid && fo < Fo && to < To) Vec<T>::load(dzb + ((size_t)fo * To + to) * C + lc0, v);
+      else {
+#pragma unroll
+        for (int i = 0; i < VG; ++i) v[i] = 0.f;
+      }
+      float* dst = s_g + (size_t)pix * CC + lv * VG;
+#pragma unroll
+      for (int q = 0; q < VG / 4; ++q)
+        *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+    __syncthreads();
+    if (cvalid) {
+      for (int strip = part; strip < STRIPS; strip += PARTS) {
+        const int fl = strip / SPR, ts = strip - fl * SPR;
+        float g[P][VW];
+#pragma unroll
+        for (int pp = 0; pp < P; ++pp) {
+          const float* gp = s_g + ((size_t)fl * TT + ts * P + pp) * CC + cw * VW;
+#pragma unroll
+          for (int i = 0; i < VW; ++i) g[pp][i] = gp[i];
+        }
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+          const float* rowp = s_in + ((size_t)(fl * S + ky) * IT + ts * P * S) * CC + cw * VW;
+#pragma unroll
+          for (int ix = 0; ix < NIN; ++ix) {
+            float v[VW];
+#pragma unroll
+            for (int i = 0; i < VW; ++i) v[i] = rowp[(size_t)ix * CC + i];
+#pragma unroll
+            for (int pp = 0; pp < P; ++pp) {
+              const int kx = ix - pp * S;
+              if (kx >= 0 && kx < K) {
+#pragma unroll
+                for (int i = 0; i < VW; ++i) acc[ky * K + kx][i] = fmaf(g[pp][i], v[i], acc[ky * K + kx][i]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  if (cvalid) {
+#pragma unroll
+    for (int q = 0; q < KK; ++q)
+#pragma unroll
+      for (int i = 0; i < VW; ++i) atomicAdd(&s_acc[q * CC + cw * VW + i], acc[q][i]);
+  }
+  __syncthreads();
+  float* dwb = dw + (size_t)b * dw_bstride;
+  for (int i = tid; i < KK * CC; i += kThreads) {
+    const int q = i / CC, c = i % CC;
+    if (cbase + c < C) atomicAdd(dwb + (size_t)(cbase + c) * KK + q, s_acc[i]);
+  }
+}
+
 // stem wgrad: dw[c, ky, kx] += sum dz[b,fo,to,c] * x[b, fo*s-1+ky, to*s-1+kx]
 template <typename T>
 __global__ void __launch_bounds__(kThreads) stem_wgrad_kernel(const T* __restrict__ dz, const float* __restrict__ x,
@@ -417,14 +555,19 @@ int launch_dw_bwd(int which, const void* dz, const float* wt, const void* in, In
     else { eat_set_error("dw dgrad: only k in {3,5}, stride in {1,2}"); return EAT_ERR_UNSUPPORTED; }
 #undef EAT_DG
   } else {
-    const int tcv = cv < kThreads ? cv : kThreads, ppb = kThreads / tcv;
-    dim3 grid(grid2(Fo * ceil_div(To, 8), ppb, B), B);
-    size_t smem = (size_t)k * k * C * sizeof(float);
-    if (smem > 200 * 1024) { eat_set_error("dw wgrad: channel count too large for the shared accumulator"); return EAT_ERR_UNSUPPORTED; }
-#define EAT_WG(KK, SS)                                                                                         \
-  do {                                                                                                         \
-    cudaFuncSetAttribute(dw_wgrad_kernel<T, KK, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
-    dw_wgrad_kernel<T, KK, SS><<<grid, kThreads, smem, st>>>((const T*)dz, (const T*)in, xf, dw, F, Tn, Fo, To, C); \
+    const int FR = stride == 1 ? 8 : 4, TT = stride == 1 ? 32 : 16;
+    const int IR = (FR - 1) * stride + k, IT = (TT - 1) * stride + k;
+    const int chunks = ceil_div(C, 32);
+    const int tiles = ceil_div(Fo, FR) * ceil_div(To, TT);
+    int groups = max(1, (148 * 4) / max(B * chunks, 1));
+    if (groups > tiles) groups = tiles;
+    dim3 grid(chunks * groups, B);
+    size_t smem = ((size_t)IR * IT * 32 + (size_t)FR * TT * 32 + (size_t)k * k * 32) * sizeof(float);
+#define EAT_WG(KK, SS)                                                                                          \
+  do {                                                                                                          \
+    static bool attr = false;                                                                                   \
+    if (!attr) { cudaFuncSetAttribute(dw_wgrad_tile_kernel<T, KK, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); attr = true; } \
+    dw_wgrad_tile_kernel<T, KK, SS><<<grid, kThreads, smem, st>>>((const T*)dz, (const T*)in, xf, dw, F, Tn, Fo, To, C, 0); \
   } while (0)
     if (k == 3 && stride == 1) EAT_WG(3, 1); else if (k == 3 && stride == 2) EAT_WG(3, 2);
     else if (k == 5 && stride == 1) EAT_WG(5, 1); else if (k == 5 && stride == 2) EAT_WG(5, 2);

@@ -20,6 +20,7 @@ __host__ __device__ inline long long ceil_div_ll(long long a, long long b) { ret
 __device__ __forceinline__ float act_fwd(float v, int act) {
   if (act == EAT_ACT_RELU) return fmaxf(v, 0.f);
   if (act == EAT_ACT_HSWISH) return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+  if (act == EAT_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
   return v;
 }
 // derivative of the activation w.r.t. its input, evaluated at pre-activation v

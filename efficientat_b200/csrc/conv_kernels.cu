@@ -12,6 +12,27 @@ namespace {
 
 constexpr int kThreads = 256;
 
+// 4 consecutive channels <-> fp32 registers, for either storage type (16 B fp32 / 8 B bf16)
+template <typename T> struct Vec4IO;
+template <> struct Vec4IO<float> {
+  __device__ __forceinline__ static void load(const float* p, float (&v)[4]) { Vec<float>::load(p, v); }
+  __device__ __forceinline__ static void store(float* p, const float (&v)[4]) { Vec<float>::store(p, v); }
+};
+template <> struct Vec4IO<__nv_bfloat16> {
+  __device__ __forceinline__ static void load(const __nv_bfloat16* p, float (&v)[4]) {
+    uint2 t = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+    float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  __device__ __forceinline__ static void store(__nv_bfloat16* p, const float (&v)[4]) {
+    uint2 t;
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    t.x = *reinterpret_cast<uint32_t*>(&a); t.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = t;
+  }
+};
+
 // ------------------------------------------------------------------------------------------
 // Block-level reduction of per-thread channel partial sums.
 // Thread layout: cvi = tid % cv (channel vector), slot = tid / cv.  s_acc has C floats (x2 if sq).
@@ -96,12 +117,23 @@ __global__ void __launch_bounds__(kThreads) stem_kernel(
 // convolution with the kernel flipped).  Each thread: one channel vector, a strip of P output columns whose
 // input span ((P-1)*S + K vectors per kernel row) is loaded/transformed once and reused by all taps.
 // grid = (chunks, B) so per-(sample, channel) pooling stays inside a CTA column.
+// DyMN extras for the depthwise kernel (reference models/dymn/dy_block.py): per-sample mixed weights
+// (DynamicConv :111-127), DyReLU-B (:172-188) and coordinate attention (:195-201) as a register-resident epilogue.
+struct DyEpi {
+  const float* theta;    // [B, C, 4] sigmoid(coef_net(h_c)) or nullptr
+  const float* lam;      // [4] lambdas
+  const float* init;     // [4] init_v
+  const float* ca_f;     // [B, Fo, C] sigmoid(g_cf) or nullptr
+  const float* ca_t;     // [B, To, C] sigmoid(g_ct)
+  long long wt_bstride;  // floats between the weight tables of consecutive samples (0: shared weights)
+};
+
 template <typename T, int K, int S>
 __global__ void __launch_bounds__(kThreads, 2) dw_kernel(
     const T* __restrict__ in, const float* __restrict__ wt, T* __restrict__ out,
     int F, int Tn, int Fo, int To, int C, InXform xf,
     const float* __restrict__ scale, const float* __restrict__ shift, int act, const T* __restrict__ res, int flip,
-    float* __restrict__ pool /*[B,C] or null*/, double* __restrict__ stat_sum, double* __restrict__ stat_sq) {
+    float* __restrict__ pool /*[B,C] or null*/, double* __restrict__ stat_sum, double* __restrict__ stat_sq, DyEpi dy) {
   constexpr int V = Vec<T>::N;
   constexpr int P = (S == 1 && V == 4) ? 8 : 4;
   constexpr int NIN = (P - 1) * S + K;
@@ -125,6 +157,7 @@ __global__ void __launch_bounds__(kThreads, 2) dw_kernel(
   const T* inb = in + (size_t)b * F * Tn * C;
   T* outb = out + (size_t)b * Fo * To * C;
   const T* resb = res != nullptr ? res + (size_t)b * Fo * To * C : nullptr;
+  wt += (size_t)b * dy.wt_bstride;
   // channel vectors beyond kThreads are covered by looping cvi
   for (int cvi = threadIdx.x % (cv < kThreads ? cv : kThreads); cvi < cv; cvi += kThreads) {
     const int slot = cv < kThreads ? threadIdx.x / cv : 0;
@@ -134,6 +167,18 @@ __global__ void __launch_bounds__(kThreads, 2) dw_kernel(
     if (xf.scale != nullptr) {
 #pragma unroll
       for (int i = 0; i < V; ++i) { isc[i] = xf.scale[c0 + i]; ish[i] = xf.shift[c0 + i]; }
+    }
+    float da1[V], da2[V], db1[V], db2[V];
+    if (dy.theta != nullptr) {
+      const float* th = dy.theta + ((size_t)b * C + c0) * 4;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float4 t4 = __ldg(reinterpret_cast<const float4*>(th) + i);
+        da1[i] = (2.f * t4.x - 1.f) * dy.lam[0] + dy.init[0];
+        da2[i] = (2.f * t4.y - 1.f) * dy.lam[1] + dy.init[1];
+        db1[i] = (2.f * t4.z - 1.f) * dy.lam[2] + dy.init[2];
+        db2[i] = (2.f * t4.w - 1.f) * dy.lam[3] + dy.init[3];
+      }
     }
     for (int u = blockIdx.x * ppb + slot; u < units; u += gridDim.x * ppb) {
       const int fo = u / strips;
@@ -191,6 +236,19 @@ __global__ void __launch_bounds__(kThreads, 2) dw_kernel(
 #pragma unroll
           for (int i = 0; i < V; ++i) { o[i] = acc[p][i]; lsum[i] += o[i]; lsq[i] = fmaf(o[i], o[i], lsq[i]); }
         }
+        if (dy.theta != nullptr) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) o[i] = fmaxf(fmaf(o[i], da1[i], db1[i]), fmaf(o[i], da2[i], db2[i]));
+        }
+        if (dy.ca_f != nullptr) {
+          const float* cf = dy.ca_f + ((size_t)b * Fo + fo) * C + c0;
+          const float* ct = dy.ca_t + ((size_t)b * To + to) * C + c0;
+#pragma unroll
+          for (int q = 0; q < V / 4; ++q) {
+            const float4 f4 = __ldg(reinterpret_cast<const float4*>(cf) + q), t4 = __ldg(reinterpret_cast<const float4*>(ct) + q);
+            o[4 * q] *= f4.x * t4.x; o[4 * q + 1] *= f4.y * t4.y; o[4 * q + 2] *= f4.z * t4.z; o[4 * q + 3] *= f4.w * t4.w;
+          }
+        }
         const size_t off = ((size_t)fo * To + to) * C + c0;
         if (resb != nullptr) {
           float r[V];
@@ -215,6 +273,195 @@ __global__ void __launch_bounds__(kThreads, 2) dw_kernel(
     for (int c = threadIdx.x; c < C; c += kThreads) {
       if (pool != nullptr) atomicAdd(pool + (size_t)b * C + c, s_sum[c]);
       if (stat_sum != nullptr) { atomicAdd(stat_sum + c, (double)s_sum[c]); atomicAdd(stat_sq + c, (double)s_sq[c]); }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Shared-memory tiled depthwise convolution (same contract as dw_kernel).  A CTA stages an input tile
+// ((FR-1)*S+K rows x (TT-1)*S+K columns x 32 channels) in shared memory as fp32, applying the producing layer's
+// BatchNorm + activation ONCE per element (the register-strip kernel re-applies it for every kernel row), then
+// every thread computes a strip of P outputs for one 4-channel vector from shared memory (LDS.128).
+template <typename T, int K, int S>
+__global__ void __launch_bounds__(kThreads) dw_tile_kernel(
+    const T* __restrict__ in, const float* __restrict__ wt, T* __restrict__ out,
+    int F, int Tn, int Fo, int To, int C, InXform xf,
+    const float* __restrict__ scale, const float* __restrict__ shift, int act, const T* __restrict__ res, int flip,
+    float* __restrict__ pool, double* __restrict__ stat_sum, double* __restrict__ stat_sq, DyEpi dy) {
+  constexpr int VG = Vec<T>::N;                 // channels per 16-byte global vector
+  constexpr int CC = 32;                        // channels per tile
+  constexpr int CCV = CC / 4;
+  constexpr int FR = (S == 1) ? 8 : 4;
+  constexpr int TT = (S == 1) ? 32 : 16;
+  constexpr int P = (S == 1) ? 8 : 2;
+  constexpr int SPR = TT / P;
+  constexpr int IR = (FR - 1) * S + K, IT = (TT - 1) * S + K;
+  constexpr int NIN = (P - 1) * S + K;
+  constexpr int PAD = (K - 1) / 2;
+  constexpr int ITEMS = FR * SPR * CCV;
+  static_assert(ITEMS % kThreads == 0 || ITEMS < kThreads || true, "");
+  extern __shared__ __align__(16) float smem[];
+  float* s_in = smem;                           // [IR*IT][CC]
+  float* s_w = s_in + IR * IT * CC;             // [K*K][CC]
+  float* s_sum = s_w + K * K * CC;              // [CC]
+  float* s_sq = s_sum + CC;                     // [CC]
+  const int b = blockIdx.y;
+  const int tiles_t = ceil_div(To, TT), tiles_f = ceil_div(Fo, FR), chunks = ceil_div(C, CC);
+  const int tiles_per_chunk = tiles_t * tiles_f;
+  const bool need_red = (pool != nullptr) || (stat_sum != nullptr);
+  const T* inb = in + (size_t)b * F * Tn * C;
+  T* outb = out + (size_t)b * Fo * To * C;
+  const T* resb = res != nullptr ? res + (size_t)b * Fo * To * C : nullptr;
+  wt += (size_t)b * dy.wt_bstride;
+  const int tid = threadIdx.x;
+  // blockIdx.x enumerates (channel chunk, tile group); each CTA walks its tile group with a stride
+  const int groups = gridDim.x / chunks;        // CTAs per channel chunk
+  const int chunk = blockIdx.x / groups, grp = blockIdx.x - chunk * groups;
+  if (chunk >= chunks) return;
+  const int cbase = chunk * CC;
+  const int ccv_valid = min(CC, C - cbase) / 4; // valid 4-channel vectors in this chunk
+  // ---- weights + reduction scratch
+  for (int i = tid; i < K * K * CC; i += kThreads) {
+    const int tap = i / CC, c = i % CC;
+    const int src = flip ? (K * K - 1 - tap) : tap;
+    s_w[i] = (cbase + c < C) ? __ldg(wt + (size_t)src * C + cbase + c) : 0.f;
+  }
+  if (tid < 2 * CC) s_sum[tid] = 0.f;
+  // loader mapping: VPP 16-byte vectors per pixel
+  constexpr int VPP = CC / VG;
+  const int lv = tid % VPP;                     // this thread's vector slot inside a pixel (fixed)
+  const int lc0 = cbase + lv * VG;              // first channel of that vector
+  const bool lvalid = lc0 < C;
+  float isc[VG], ish[VG];
+  if (xf.scale != nullptr && lvalid) {
+#pragma unroll
+    for (int i = 0; i < VG; ++i) { isc[i] = xf.scale[lc0 + i]; ish[i] = xf.shift[lc0 + i]; }
+  }
+  // compute mapping
+  const int cvec = tid % CCV;
+  const int c0 = cbase + cvec * 4;
+  const bool cvalid = cvec < ccv_valid;
+  float osc[4], osh[4], lsum[4] = {0.f, 0.f, 0.f, 0.f}, lsq[4] = {0.f, 0.f, 0.f, 0.f};
+  float da1[4], da2[4], db1[4], db2[4];
+  if (cvalid) {
+    if (scale != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { osc[i] = scale[c0 + i]; osh[i] = shift[c0 + i]; }
+    }
+    if (dy.theta != nullptr) {
+      const float* th = dy.theta + ((size_t)b * C + c0) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 t4 = __ldg(reinterpret_cast<const float4*>(th) + i);
+        da1[i] = (2.f * t4.x - 1.f) * dy.lam[0] + dy.init[0];
+        da2[i] = (2.f * t4.y - 1.f) * dy.lam[1] + dy.init[1];
+        db1[i] = (2.f * t4.z - 1.f) * dy.lam[2] + dy.init[2];
+        db2[i] = (2.f * t4.w - 1.f) * dy.lam[3] + dy.init[3];
+      }
+    }
+  }
+  for (int tile = grp; tile < tiles_per_chunk; tile += groups) {
+    const int tf = tile / tiles_t, tt = tile - tf * tiles_t;
+    const int f0 = tf * FR, t0 = tt * TT;
+    __syncthreads();                            // previous tile's readers are done (also covers the init above)
+    // ---- stage the input tile (transform once)
+    for (int idx = tid; idx < IR * IT * VPP; idx += kThreads) {
+      const int pix = idx / VPP;
+      const int ir = pix / IT, it = pix - ir * IT;
+      const int f = f0 * S - PAD + ir, t = t0 * S - PAD + it;
+      float v[VG];
+      if (lvalid && f >= 0 && f < F && t >= 0 && t < Tn) {
+        Vec<T>::load(inb + ((size_t)f * Tn + t) * C + lc0, v);
+        if (xf.scale != nullptr) {
+#pragma unroll
+          for (int i = 0; i < VG; ++i) v[i] = act_fwd(fmaf(v[i], isc[i], ish[i]), xf.act);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < VG; ++i) v[i] = 0.f;
+      }
+      float* dst = s_in + (size_t)pix * CC + lv * VG;
+#pragma unroll
+      for (int q = 0; q < VG / 4; ++q)
+        *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+    __syncthreads();
+    // ---- compute
+    if (cvalid) {
+      for (int item = tid; item < ITEMS; item += kThreads) {
+        const int strip = item / CCV;
+        const int fl = strip / SPR, ts = strip - fl * SPR;
+        const int fo = f0 + fl, to0 = t0 + ts * P;
+        if (fo >= Fo || to0 >= To) continue;
+        float acc[P][4];
+#pragma unroll
+        for (int p = 0; p < P; ++p) { acc[p][0] = acc[p][1] = acc[p][2] = acc[p][3] = 0.f; }
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+          float4 w4[K];
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) w4[kx] = *reinterpret_cast<const float4*>(s_w + (ky * K + kx) * CC + cvec * 4);
+          const float* rowp = s_in + ((size_t)(fl * S + ky) * IT + ts * P * S) * CC + cvec * 4;
+#pragma unroll
+          for (int ix = 0; ix < NIN; ++ix) {
+            const float4 v = *reinterpret_cast<const float4*>(rowp + (size_t)ix * CC);
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+              const int kx = ix - p * S;
+              if (kx >= 0 && kx < K) {
+                acc[p][0] = fmaf(v.x, w4[kx].x, acc[p][0]);
+                acc[p][1] = fmaf(v.y, w4[kx].y, acc[p][1]);
+                acc[p][2] = fmaf(v.z, w4[kx].z, acc[p][2]);
+                acc[p][3] = fmaf(v.w, w4[kx].w, acc[p][3]);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          const int to = to0 + p;
+          if (to >= To) break;
+          float o[4];
+          if (scale != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { o[i] = act_fwd(fmaf(acc[p][i], osc[i], osh[i]), act); lsum[i] += o[i]; }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { o[i] = acc[p][i]; lsum[i] += o[i]; lsq[i] = fmaf(o[i], o[i], lsq[i]); }
+          }
+          if (dy.theta != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = fmaxf(fmaf(o[i], da1[i], db1[i]), fmaf(o[i], da2[i], db2[i]));
+          }
+          if (dy.ca_f != nullptr) {
+            const float4 f4 = __ldg(reinterpret_cast<const float4*>(dy.ca_f + ((size_t)b * Fo + fo) * C + c0));
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(dy.ca_t + ((size_t)b * To + to) * C + c0));
+            o[0] *= f4.x * t4.x; o[1] *= f4.y * t4.y; o[2] *= f4.z * t4.z; o[3] *= f4.w * t4.w;
+          }
+          const size_t off = ((size_t)fo * To + to) * C + c0;
+          if (resb != nullptr) {
+            float r[4];
+            Vec4IO<T>::load(resb + off, r);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] += r[i];
+          }
+          Vec4IO<T>::store(outb + off, o);
+        }
+      }
+    }
+  }
+  if (need_red) {
+    if (cvalid) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        atomicAdd(&s_sum[cvec * 4 + i], lsum[i]);
+        if (stat_sum != nullptr) atomicAdd(&s_sq[cvec * 4 + i], lsq[i]);
+      }
+    }
+    __syncthreads();
+    if (tid < CC && cbase + tid < C) {
+      if (pool != nullptr) atomicAdd(pool + (size_t)b * C + cbase + tid, s_sum[tid]);
+      if (stat_sum != nullptr) { atomicAdd(stat_sum + cbase + tid, (double)s_sum[tid]); atomicAdd(stat_sq + cbase + tid, (double)s_sq[tid]); }
     }
   }
 }
@@ -378,20 +625,26 @@ inline int grid_for(long long items, int per_block, int max_blocks = 148 * 16) {
 template <typename T>
 int launch_dw(const T* in, const float* wt, T* out, int B, int F, int Tn, int C, int k, int stride, InXform xf,
               const float* scale, const float* shift, int act, const T* res, int flip, float* pool, double* ssum,
-              double* ssq, cudaStream_t st) {
+              double* ssq, cudaStream_t st, DyEpi dy = DyEpi{nullptr, nullptr, nullptr, nullptr, nullptr, 0}) {
   constexpr int V = Vec<T>::N;
   if (C % V != 0) { eat_set_error("dw conv: channels must be a multiple of the vector width"); return EAT_ERR_ARG; }
   const int pad = (k - 1) / 2;
   const int Fo = (F + 2 * pad - k) / stride + 1, To = (Tn + 2 * pad - k) / stride + 1;
-  const int cv = C / V;
-  const int ppb = kThreads / cv > 0 ? kThreads / cv : 1;
-  const int units = Fo * ceil_div(To, (stride == 1 && V == 4) ? 8 : 4);
-  int gx = ceil_div(units, ppb);
-  const int cap = max(1, (148 * 8) / max(B, 1));
-  if (gx > cap) gx = cap;   // grid-stride over strips; keeps per-CTA reductions coarse
-  dim3 grid(gx, B);
-  size_t smem = 2 * (size_t)C * sizeof(float);
-#define EAT_DW(KK, SS) dw_kernel<T, KK, SS><<<grid, kThreads, smem, st>>>(in, wt, out, F, Tn, Fo, To, C, xf, scale, shift, act, res, flip, pool, ssum, ssq)
+  // shared-memory tiled kernel: grid.x = channel chunks x tile groups (each CTA strides over its group's tiles)
+  const int FR = stride == 1 ? 8 : 4, TT = stride == 1 ? 32 : 16;
+  const int IR = (FR - 1) * stride + k, IT = (TT - 1) * stride + k;
+  const int chunks = ceil_div(C, 32);
+  const int tiles = ceil_div(Fo, FR) * ceil_div(To, TT);
+  int groups = max(1, (148 * 6) / max(B * chunks, 1));
+  if (groups > tiles) groups = tiles;
+  dim3 grid(chunks * groups, B);
+  size_t smem = ((size_t)IR * IT * 32 + (size_t)k * k * 32 + 64) * sizeof(float);
+#define EAT_DW(KK, SS)                                                                                          \
+  do {                                                                                                          \
+    static bool attr = false;                                                                                   \
+    if (!attr) { cudaFuncSetAttribute(dw_tile_kernel<T, KK, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; } \
+    dw_tile_kernel<T, KK, SS><<<grid, kThreads, smem, st>>>(in, wt, out, F, Tn, Fo, To, C, xf, scale, shift, act, res, flip, pool, ssum, ssq, dy); \
+  } while (0)
   if (k == 3 && stride == 1) EAT_DW(3, 1);
   else if (k == 3 && stride == 2) EAT_DW(3, 2);
   else if (k == 5 && stride == 1) EAT_DW(5, 1);
@@ -441,6 +694,20 @@ int eat_dw_conv_fwd(const void* in, const float* wt, void* out, int dtype, int B
   if (dtype == EAT_BF16)
     return launch_dw<__nv_bfloat16>((const __nv_bfloat16*)in, wt, (__nv_bfloat16*)out, B, F, T, C, k, stride, xf, scale, shift, act, nullptr, 0, pool, stat_sum, stat_sq, st);
   return launch_dw<float>((const float*)in, wt, (float*)out, B, F, T, C, k, stride, xf, scale, shift, act, nullptr, 0, pool, stat_sum, stat_sq, st);
+}
+
+// DyMN depthwise stage: per-sample weight tables + BN affine + DyReLU-B + coordinate attention in one kernel
+int eat_dw_conv_fwd_dy(const void* in, const float* wt, long long wt_bstride, void* out, int dtype, int B, int F, int T,
+                       int C, int k, int stride, const float* in_scale, const float* in_shift, int in_act,
+                       const float* scale, const float* shift, const float* theta, const float* lam,
+                       const float* init, const float* ca_f, const float* ca_t, double* stat_sum, double* stat_sq,
+                       cudaStream_t st) {
+  if (B == 0) return EAT_OK;
+  InXform xf{in_scale, in_shift, nullptr, in_act, 0};
+  DyEpi dy{theta, lam, init, ca_f, ca_t, wt_bstride};
+  if (dtype == EAT_BF16)
+    return launch_dw<__nv_bfloat16>((const __nv_bfloat16*)in, wt, (__nv_bfloat16*)out, B, F, T, C, k, stride, xf, scale, shift, 0, nullptr, 0, nullptr, stat_sum, stat_sq, st, dy);
+  return launch_dw<float>((const float*)in, wt, (float*)out, B, F, T, C, k, stride, xf, scale, shift, 0, nullptr, 0, nullptr, stat_sum, stat_sq, st, dy);
 }
 
 // stride-1 depthwise data gradient = the forward kernel with mirrored taps (+ residual-gradient add)

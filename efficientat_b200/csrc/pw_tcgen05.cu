@@ -48,7 +48,22 @@ struct TcParams {
   double* stat_sq;
   int BN;        // columns per N tile (multiple of 16)
   int n_tiles, m_tiles, k_blocks;
+  // DynamicConv (reference models/dymn/dy_block.py:103-131): per-sample weights W_b = sum_k att[b,k] * W[k],
+  // mixed while the weight tile is staged.  Tiles then never straddle samples.
+  const float* dyn_att;   // [B, dyn_k] or nullptr
+  int dyn_k;              // number of kernels (4)
+  int tps;                // M tiles per sample (0: flat tiling over all rows)
+  int tile_rps;           // rows per sample used for tiling
 };
+
+// first row / row limit / sample of M tile `mt`
+__device__ __forceinline__ void tile_rows(const TcParams& p, int mt, long long& m0, long long& m_lim, int& b) {
+  if (p.tps == 0) { m0 = (long long)mt * BM; m_lim = p.M; b = 0; return; }
+  b = mt / p.tps;
+  const int j = mt - b * p.tps;
+  m0 = (long long)b * p.tile_rps + (long long)j * BM;
+  m_lim = (long long)(b + 1) * p.tile_rps;
+}
 
 using namespace tc;
 
@@ -94,6 +109,7 @@ template <> struct OutVec<__nv_bfloat16> {
 __device__ __forceinline__ float act_sel(float v, int act) {     // branch-free activation
   const float r = fmaxf(v, 0.f);
   const float h = v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+  if (act == EAT_ACT_SIGMOID) return 1.f / (1.f + expf(-v));      // rare (DyMN context nets): uniform branch
   return act == EAT_ACT_HSWISH ? h : (act == EAT_ACT_RELU ? r : v);
 }
 
@@ -142,7 +158,14 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
     int it = 0;                                                    // global (tile, k-block) counter of this CTA
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;       // m fastest: a CTA stays on one N tile
-      const long long m0 = (long long)mt * BM;
+      long long m0, m_lim;
+      int bsample;
+      tile_rows(p, mt, m0, m_lim, bsample);
+      float datt[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p.dyn_att != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) datt[j] = j < p.dyn_k ? __ldg(p.dyn_att + (size_t)bsample * p.dyn_k + j) : 0.f;
+      }
       const int n0 = nt * BN;
       const int b0 = p.xf.gate != nullptr ? (int)(m0 / rps) : 0;
       const int off0 = p.xf.gate != nullptr ? (int)(m0 - (long long)b0 * rps) : 0;
@@ -175,7 +198,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
           for (int i = 0; i < 4; ++i) {
             const int row = rb + i * rstep;
             const long long m = m0 + row;
-            if (kok && row < BM && m < p.M) load_chunk<T>(A + m * K + k, av[i]);
+            if (kok && row < BM && m < m_lim) load_chunk<T>(A + m * K + k, av[i]);
             else {
 #pragma unroll
               for (int j = 0; j < 8; ++j) av[i][j] = 0.f;
@@ -186,7 +209,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
             const int row = rb + i * rstep;
             const long long m = m0 + row;
             if (row >= BM || !kact) continue;
-            if (kok && m < p.M) {
+            if (kok && m < m_lim) {
               if (p.xf.scale != nullptr) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) av[i][j] = act_sel(fmaf(av[i][j], isc[j], ish[j]), p.xf.act);
@@ -210,8 +233,19 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
           for (int i = 0; i < 4; ++i) {
             const int r = rb + i * rstep;
             const int n = n0 + r;
-            if (kok && r < BN && n < N) load_chunk<float>(p.W + (size_t)n * K + k, wv[i]);
-            else {
+            if (kok && r < BN && n < N) {
+              if (p.dyn_att == nullptr) load_chunk<float>(p.W + (size_t)n * K + k, wv[i]);
+              else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) wv[i][j] = 0.f;
+                for (int kk = 0; kk < p.dyn_k; ++kk) {
+                  float t8[8];
+                  load_chunk<float>(p.W + (size_t)kk * N * K + (size_t)n * K + k, t8);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) wv[i][j] = fmaf(datt[kk], t8[j], wv[i][j]);
+                }
+              }
+            } else {
 #pragma unroll
               for (int j = 0; j < 8; ++j) wv[i][j] = 0.f;
             }
@@ -282,7 +316,9 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
     const bool do_stats = p.stat_sum != nullptr;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;
-      const long long m0 = (long long)mt * BM;
+      long long m0, m_lim;
+      int bsample;
+      tile_rows(p, mt, m0, m_lim, bsample);
       const int n0 = nt * BN;
       if (nt != cur_nt) {
         // new N tile: flush the previous tile's statistics, stage this tile's epilogue affine
@@ -330,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const long long m = mrow0 + i * 4 + rg;
-            if (nok && m < p.M) OutVec<T>::load(R + m * N + n, res[i]);
+            if (nok && m < m_lim) OutVec<T>::load(R + m * N + n, res[i]);
             else { res[i][0] = res[i][1] = res[i][2] = res[i][3] = 0.f; }
           }
         }
@@ -341,7 +377,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
           const long long m = mrow0 + row;
           const float4 v4 = *reinterpret_cast<const float4*>(stg + row * STG_LD + col4);
           float v[4] = {v4.x, v4.y, v4.z, v4.w};
-          if (m < p.M) {
+          if (m < m_lim) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) { cs[j] += v[j]; cq[j] = fmaf(v[j], v[j], cq[j]); }
             if (nok) {
@@ -403,7 +439,13 @@ int launch_tc(const TcParams& p0, cudaStream_t st) {
   p.n_tiles = ceil_div(p.N, BN_MAX);
   p.BN = ceil_div(ceil_div(p.N, p.n_tiles), 16) * 16;
   p.n_tiles = ceil_div(p.N, p.BN);
-  p.m_tiles = ceil_div(p.M, BM);
+  if (p.dyn_att != nullptr) {
+    p.tps = ceil_div(p.tile_rps, BM);
+    p.m_tiles = (p.M / p.tile_rps) * p.tps;
+  } else {
+    p.tps = 0;
+    p.m_tiles = ceil_div(p.M, BM);
+  }
   p.k_blocks = ceil_div(p.K, BK);
   constexpr size_t smem = (size_t)STAGES * NP * (A_TILE_BYTES + BN_MAX * 128) + 8 * 32 * STG_LD * sizeof(float) +
                           2 * BN_MAX * sizeof(float) + 16 * BN_MAX * sizeof(float) +
@@ -441,7 +483,28 @@ extern "C" int eat_pw_tc_fwd(const void* A, int a_dtype, const float* W, int w_t
   p.A = A; p.W = W; p.C = C; p.residual = residual; p.M = (int)M; p.N = N; p.K = K;
   p.xf = InXform{in_scale, in_shift, gate, in_act, rows_per_sample > 0 ? rows_per_sample : 1};
   p.scale = scale; p.shift = shift; p.act = act; p.stat_sum = stat_sum; p.stat_sq = stat_sq;
+  p.dyn_att = nullptr; p.dyn_k = 0; p.tps = 0; p.tile_rps = 0;
   if (a_dtype == EAT_BF16) return launch_tc<__nv_bfloat16, 1, 3, 256>(p, st);
+  return launch_tc<float, 2, 2, 128>(p, st);
+}
+
+// DynamicConv 1x1 (reference models/dymn/dy_block.py:103-131): W holds dyn_k kernels [dyn_k][N][K]; sample b uses
+// sum_k att[b,k] * W[k].  M = B * rows_per_sample; rows of a tile never cross a sample.
+extern "C" int eat_pw_tc_dyn_fwd(const void* A, int dtype, const float* W, const float* att, int dyn_k, void* C,
+                                 long long M, int N, int K, int rows_per_sample, const float* in_scale,
+                                 const float* in_shift, int in_act, const float* scale, const float* shift, int act,
+                                 const void* residual, double* stat_sum, double* stat_sq, cudaStream_t st) {
+  if (M == 0) return EAT_OK;
+  if (dyn_k < 1 || dyn_k > 4) { eat_set_error("pw_tc_dyn: 1..4 kernels supported"); return EAT_ERR_UNSUPPORTED; }
+  if (rows_per_sample < 1 || M % rows_per_sample != 0) { eat_set_error("pw_tc_dyn: M must be B * rows_per_sample"); return EAT_ERR_ARG; }
+  if (K % 8 != 0 || N % 8 != 0) { eat_set_error("pw_tc_dyn: K and N must be multiples of 8"); return EAT_ERR_ARG; }
+  if (M >= (1ll << 31) - BM) { eat_set_error("pw_tc_dyn: M too large"); return EAT_ERR_ARG; }
+  TcParams p;
+  p.A = A; p.W = W; p.C = C; p.residual = residual; p.M = (int)M; p.N = N; p.K = K;
+  p.xf = InXform{in_scale, in_shift, nullptr, in_act, rows_per_sample};
+  p.scale = scale; p.shift = shift; p.act = act; p.stat_sum = stat_sum; p.stat_sq = stat_sq;
+  p.dyn_att = att; p.dyn_k = dyn_k; p.tile_rps = rows_per_sample; p.tps = 1;
+  if (dtype == EAT_BF16) return launch_tc<__nv_bfloat16, 1, 3, 256>(p, st);
   return launch_tc<float, 2, 2, 128>(p, st);
 }
 

@@ -189,40 +189,55 @@ class MNEngine:
                    sc[1].data_ptr(), ACT["hswish"], 0, 0, st)
         keep(a, Fi, Ti, c0)
         for blk in self.blocks:
-            inp = a
-            M = B * Fi * Ti
-            if blk.expand is not None:
-                e = torch.empty(B, Fi, Ti, blk.cexp, device=dev, dtype=td)
-                self._gemm(inp, blk.expand[0].weight, e, M, blk.cexp, blk.cin, sc=self._fold(blk.expand[1], dev),
-                           act=blk.act)
-            else:
-                e = inp
-            Fo, To = _conv_out(Fi, blk.k, blk.stride), _conv_out(Ti, blk.k, blk.stride)
-            d = torch.empty(B, Fo, To, blk.cexp, device=dev, dtype=td)
-            sc = self._fold(blk.dw[1], dev)
-            pool = torch.zeros(B, blk.cexp, device=dev, dtype=torch.float32) if blk.se is not None else None
-            L.dw_conv_fwd(e.data_ptr(), self._dw_weights(blk.dw[0], dev).data_ptr(), d.data_ptr(), dc, B, Fi, Ti,
-                          blk.cexp, blk.k, blk.stride, 0, 0, 0, sc[0].data_ptr(), sc[1].data_ptr(), blk.act,
-                          _ptr(pool), 0, 0, st)
-            gate = None
-            if blk.se is not None:
-                gate = torch.empty(B, blk.cexp, device=dev, dtype=torch.float32)
-                S = blk.se.fc1.out_features
-                L.se_fc_fwd(pool.data_ptr(), 1.0 / (Fo * To), blk.se.fc1.weight.data_ptr(),
-                            blk.se.fc1.bias.data_ptr(), blk.se.fc2.weight.data_ptr(), blk.se.fc2.bias.data_ptr(),
-                            gate.data_ptr(), 0, B, blk.cexp, S, st)
-            Mo = B * Fo * To
-            o = torch.empty(B, Fo, To, blk.cout, device=dev, dtype=td)
-            self._gemm(d, blk.proj[0].weight, o, Mo, blk.cout, blk.cexp, gate=gate, rows_per_sample=Fo * To,
-                       sc=self._fold(blk.proj[1], dev), act=0, res=inp if blk.res else None)
-            a, Fi, Ti = o, Fo, To
+            a, Fi, Ti = self._ir_block_eval(blk, a, B, Fi, Ti)
             keep(a, Fi, Ti, blk.cout)
+        logits, feat, z = self._head_eval(a, B, Fi, Ti)
+        keep(z, Fi, Ti, self.last[0].out_channels)
+        return logits, feat, fmaps
+
+    def _ir_block_eval(self, blk, a, B, Fi, Ti):
+        """one InvertedResidual with folded BatchNorm: 3-4 launches (reference block_types.py:177-181)"""
+        L = lib()
+        dev, st = a.device, _stream()
+        td, dc = self.tdtype, self.dcode
+        inp = a
+        M = B * Fi * Ti
+        if blk.expand is not None:
+            e = torch.empty(B, Fi, Ti, blk.cexp, device=dev, dtype=td)
+            self._gemm(inp, blk.expand[0].weight, e, M, blk.cexp, blk.cin, sc=self._fold(blk.expand[1], dev),
+                       act=blk.act)
+        else:
+            e = inp
+        Fo, To = _conv_out(Fi, blk.k, blk.stride), _conv_out(Ti, blk.k, blk.stride)
+        d = torch.empty(B, Fo, To, blk.cexp, device=dev, dtype=td)
+        sc = self._fold(blk.dw[1], dev)
+        pool = torch.zeros(B, blk.cexp, device=dev, dtype=torch.float32) if blk.se is not None else None
+        L.dw_conv_fwd(e.data_ptr(), self._dw_weights(blk.dw[0], dev).data_ptr(), d.data_ptr(), dc, B, Fi, Ti,
+                      blk.cexp, blk.k, blk.stride, 0, 0, 0, sc[0].data_ptr(), sc[1].data_ptr(), blk.act,
+                      _ptr(pool), 0, 0, st)
+        gate = None
+        if blk.se is not None:
+            gate = torch.empty(B, blk.cexp, device=dev, dtype=torch.float32)
+            S = blk.se.fc1.out_features
+            L.se_fc_fwd(pool.data_ptr(), 1.0 / (Fo * To), blk.se.fc1.weight.data_ptr(),
+                        blk.se.fc1.bias.data_ptr(), blk.se.fc2.weight.data_ptr(), blk.se.fc2.bias.data_ptr(),
+                        gate.data_ptr(), 0, B, blk.cexp, S, st)
+        Mo = B * Fo * To
+        o = torch.empty(B, Fo, To, blk.cout, device=dev, dtype=td)
+        self._gemm(d, blk.proj[0].weight, o, Mo, blk.cout, blk.cexp, gate=gate, rows_per_sample=Fo * To,
+                   sc=self._fold(blk.proj[1], dev), act=0, res=inp if blk.res else None)
+        return o, Fo, To
+
+    def _head_eval(self, a, B, Fi, Ti):
+        """last 1x1 conv + BN + Hardswish, global average pool, classifier MLP (mn/model.py:160-166,187-194,220-221)"""
+        L = lib()
+        dev, st = a.device, _stream()
+        td, dc = self.tdtype, self.dcode
         conv, bn = self.last[0], self.last[1]
         cl = conv.out_channels
         M = B * Fi * Ti
         z = torch.empty(B, Fi, Ti, cl, device=dev, dtype=td)
         self._gemm(a, conv.weight, z, M, cl, conv.in_channels, sc=self._fold(bn, dev), act=ACT["hswish"])
-        keep(z, Fi, Ti, cl)
         feat = torch.zeros(B, cl, device=dev, dtype=torch.float32)
         L.bn_act_pool(z.data_ptr(), 0, 0, 0, feat.data_ptr(), 1.0 / (Fi * Ti), dc, B, Fi * Ti, cl, st)
         h = torch.empty(B, self.fc1.out_features, device=dev, dtype=torch.float32)
@@ -231,7 +246,7 @@ class MNEngine:
         logits = torch.empty(B, self.fc2.out_features, device=dev, dtype=torch.float32)
         self._gemm(h, self.fc2.weight, logits, B, self.fc2.out_features, self.fc1.out_features, bias=self.fc2.bias,
                    a_code=0, c_code=0)
-        return logits, feat, fmaps
+        return logits, feat, z
 
     # ------------------------------------------------------------------ training forward
     def _new_stats(self, c, dev):

@@ -38,6 +38,7 @@ extern "C" {
 #define EAT_ACT_NONE 0
 #define EAT_ACT_RELU 1
 #define EAT_ACT_HSWISH 2
+#define EAT_ACT_SIGMOID 3   /* forward-only (DyMN coordinate attention / DyReLU coefficient nets) */
 
 #define EAT_F32 0
 #define EAT_BF16 1
@@ -125,6 +126,33 @@ int eat_pw_tc_fwd(const void* A, int a_dtype, const float* W, int w_trans, void*
                   double* stat_sum, double* stat_sq, cudaStream_t stream);
 /* out[cols, rows] = in[rows, cols]^T (fp32); used to feed W^T to the data-gradient GEMM. */
 int eat_transpose_f32(const float* in, float* out, int rows, int cols, cudaStream_t stream);
+
+/* ---- DyMN (reference models/dymn/dy_block.py) ---- */
+
+/* DynamicConv 1x1 on tensor cores (dy_block.py:103-131): W = dyn_k kernels [dyn_k][N][K]; sample b uses
+ * sum_k att[b,k]*W[k], mixed while the weight tile is staged (never materialised).  M = B*rows_per_sample. */
+int eat_pw_tc_dyn_fwd(const void* A, int dtype, const float* W, const float* att, int dyn_k, void* C, long long M,
+                      int N, int K, int rows_per_sample, const float* in_scale, const float* in_shift, int in_act,
+                      const float* scale, const float* shift, int act, const void* residual, double* stat_sum,
+                      double* stat_sq, cudaStream_t stream);
+/* DynamicConv depthwise + BN affine + DyReLU-B (dy_block.py:172-188) + CoordAtt (:195-201) in one kernel.
+ * wt: per-sample tap-major weight tables (stride wt_bstride floats); theta [B,C,4] = sigmoid(coef_net(h_c));
+ * lam/init: DyReLU buffers; ca_f [B,Fo,C], ca_t [B,To,C] = sigmoid(g_cf), sigmoid(g_ct). */
+int eat_dw_conv_fwd_dy(const void* in, const float* wt, long long wt_bstride, void* out, int dtype, int B, int F, int T,
+                       int C, int k, int stride, const float* in_scale, const float* in_shift, int in_act,
+                       const float* scale, const float* shift, const float* theta, const float* lam,
+                       const float* init, const float* ca_f, const float* ca_t, double* stat_sum, double* stat_sq,
+                       cudaStream_t stream);
+/* ContextGen pooling (dy_block.py:236-240): out [B, F+T, C] fp32 = [mean over T | mean over F]. */
+int eat_ctx_pool(const void* x, int dtype, float* out, int B, int F, int T, int C, cudaStream_t stream);
+/* Sequence pooling of ContextGen (dy_block.py:227-233,249): AvgPool(3, stride, pad 1) or copy (stride 1) of rows
+ * [row0, row0+L) of each sample of in [B, Ltot, H] -> out [B, Lo, H]. */
+int eat_seq_pool(const float* in, float* out, int B, int Ltot, int row0, int L, int H, int stride, cudaStream_t stream);
+/* att [B,k] = softmax((Wr h_c + br)/temperature)  (dy_block.py:104-107). */
+int eat_dyconv_att(const float* hc, const float* wr, const float* br, float temperature, float* att, int B, int H, int k,
+                   cudaStream_t stream);
+/* per-sample depthwise weight tables wt [B][ksize^2][C] = sum_j att[b,j] * W[j] (dy_block.py:111-117). */
+int eat_dyconv_mix_dw(const float* w, const float* att, float* wt, int B, int C, int ksize, int k, cudaStream_t stream);
 
 /* ---- backward (training step: ex_audioset.py:197 loss.backward() over the modules above) ---- */
 

@@ -1,0 +1,81 @@
+"""GPU parity of the DyMN eval forward (ContextGen, DynamicConv, DyReLU-B, CoordAtt fused kernels) against the
+reference's golden vectors: logits within 1e-3 max-abs (fp32 activation storage), top-10 identical up to
+near-ties, per-block feature maps against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import net_oracle
+from tests.util import NETS, build_model, fmap_digest, golden, net_inputs, topk_match
+
+pytestmark = pytest.mark.gpu
+
+
+def _layer_report(tag, model, spec):
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        _, _, ref = net_oracle.dymn_forward(sd, spec, width_mult=NETS[tag][1], temperature=30.0, return_fmaps=True)
+        _, got = model(spec.cuda(), return_fmaps=True)
+    return "\n".join(f"fmap {i:2d} {tuple(r.shape)} max-abs err {(g.float().cpu() - r).abs().max().item():.3e} "
+                     f"(ref abs-max {r.abs().max().item():.3e})" for i, (r, g) in enumerate(zip(ref, got)))
+
+
+@pytest.mark.parametrize("tag", ["dymn10", "dymn04"])
+def test_dymn_eval_fp32_matches_reference_vectors(tag):
+    g = golden(tag)
+    model = build_model(tag).cuda().eval()
+    spec, _ = net_inputs(tag)
+    with torch.no_grad():
+        logits, feat = model(spec.cuda())
+    logits, feat = logits.cpu().numpy(), feat.cpu().numpy()
+    err = np.abs(logits - g["eval_logits"]).max()
+    print(f"[parity] {tag}: logit max-abs err {err:.3e}")
+    if not err < 1e-3:
+        pytest.fail(f"logit max-abs err {err}\n" + _layer_report(tag, model, spec))
+    assert np.abs(feat - g["eval_feat"]).max() < 2e-3
+    assert topk_match(logits, g["eval_logits"], 10, tie_tol=2e-4)
+
+
+def test_dymn_eval_fmaps_and_temperature():
+    tag = "dymn10"
+    g = golden(tag)
+    model = build_model(tag).cuda().eval()
+    spec, _ = net_inputs(tag)
+    with torch.no_grad():
+        _, fmaps = model(spec.cuda(), return_fmaps=True)
+    d = fmap_digest([f.float().cpu().contiguous() for f in fmaps])
+    assert d.shape == g["eval_fmaps"].shape
+    assert np.abs(d - g["eval_fmaps"]).max() < 5e-3, _layer_report(tag, model, spec)
+    # update_params(epoch) changes the attention temperature (dy_block.py:133-139) and therefore the output
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        model.update_params(12)          # T = 30 - 12 = 18 (a much lower T leaves the BN calibration far behind)
+    t = model.layers[0].depth_conv.temperature
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        logits, _ = model(spec.cuda())
+        ref, _ = net_oracle.dymn_forward(sd, spec, temperature=t)
+    assert t == 18.0
+    assert (logits.cpu() - ref).abs().max() < 1e-3 * max(1.0, ref.abs().max().item())
+    assert (logits.cpu() - torch.from_numpy(g["eval_logits"])).abs().max() > 1e-3     # the temperature matters
+
+
+def test_dymn_replace_se_variant_and_bf16():
+    from efficientat_b200.models.dymn.model import get_model
+    from efficientat_b200.synth import synth_state_
+    torch.manual_seed(0)
+    m = synth_state_(get_model(width_mult=0.4, use_dy_blocks="replace_se", verbose=False), seed=3).cuda().eval()
+    spec = net_inputs("dymn04")[0]
+    with torch.no_grad():
+        logits, feat = m(spec.cuda())
+    assert logits.shape == (2, 527) and torch.isfinite(logits).all()
+    mb = build_model("dymn10", precision="bf16").cuda().eval()
+    with torch.no_grad():
+        lb, _ = mb(net_inputs("dymn10")[0].cuda())
+    assert np.abs(lb.cpu().numpy() - golden("dymn10")["eval_logits"]).max() < 8e-2
+
+
+def test_dymn_training_mode_raises_loudly():
+    model = build_model("dymn04").cuda().train()
+    with pytest.raises(NotImplementedError):
+        model(net_inputs("dymn04")[0].cuda())
