@@ -237,94 +237,6 @@ __global__ void __launch_bounds__(kThreads) dw_dgrad_kernel(const T* __restrict_
   }
 }
 
-// wgrad: dw[c, ky, kx] += sum_{b, fo, to} dz[b,fo,to,c] * xf(in)[b, fo*S-PAD+ky, to*S-PAD+kx, c]
-// thread = (strip of P output columns, channel vector).  One kernel row ky at a time keeps the accumulators at
-// K*V registers; within a row the strip's input span ((P-1)*S + K vectors) is loaded and transformed once and
-// reused by all K taps.  Block partials are combined in shared memory, then one global atomic per (tap, channel).
-template <typename T, int K, int S>
-__global__ void __launch_bounds__(kThreads) dw_wgrad_kernel(const T* __restrict__ dz, const T* __restrict__ in,
-                                                            InXform xf, float* __restrict__ dw /*[C,1,K,K]*/,
-                                                            int F, int Tn, int Fo, int To, int C) {
-  constexpr int V = Vec<T>::N;
-  constexpr int PAD = (K - 1) / 2;
-  constexpr int KK = K * K;
-  constexpr int P = 8;
-  constexpr int NIN = (P - 1) * S + K;
-  extern __shared__ float smem[];   // [KK][C]
-  for (int i = threadIdx.x; i < KK * C; i += kThreads) smem[i] = 0.f;
-  __syncthreads();
-  const int cv = C / V;
-  const int tcv = cv < kThreads ? cv : kThreads;
-  const int ppb = kThreads / tcv;
-  const int slot = threadIdx.x / tcv;
-  const int b = blockIdx.y;
-  const T* inb = in + (size_t)b * F * Tn * C;
-  const T* dzb = dz + (size_t)b * Fo * To * C;
-  const int strips = ceil_div(To, P);
-  const int units = Fo * strips;
-  if (slot < ppb) {
-    for (int cvi = threadIdx.x % tcv; cvi < cv; cvi += tcv) {
-      const int c0 = cvi * V;
-      float isc[V], ish[V];
-      if (xf.scale != nullptr) {
-#pragma unroll
-        for (int k = 0; k < V; ++k) { isc[k] = xf.scale[c0 + k]; ish[k] = xf.shift[c0 + k]; }
-      }
-      for (int ky = 0; ky < K; ++ky) {
-        float acc[K][V];
-#pragma unroll
-        for (int q = 0; q < K; ++q)
-#pragma unroll
-          for (int k = 0; k < V; ++k) acc[q][k] = 0.f;
-        for (int u = blockIdx.x * ppb + slot; u < units; u += gridDim.x * ppb) {
-          const int fo = u / strips;
-          const int to0 = (u - fo * strips) * P;
-          const int f = fo * S - PAD + ky;
-          if (f < 0 || f >= F) continue;
-          float g[P][V];
-#pragma unroll
-          for (int pp = 0; pp < P; ++pp) {
-            if (to0 + pp < To) Vec<T>::load(dzb + ((size_t)fo * To + to0 + pp) * C + c0, g[pp]);
-            else {
-#pragma unroll
-              for (int k = 0; k < V; ++k) g[pp][k] = 0.f;
-            }
-          }
-          const T* rowp = inb + (size_t)f * Tn * C + c0;
-#pragma unroll
-          for (int ix = 0; ix < NIN; ++ix) {
-            const int t = to0 * S - PAD + ix;
-            if (t < 0 || t >= Tn) continue;
-            float v[V];
-            Vec<T>::load(rowp + (size_t)t * C, v);
-            if (xf.scale != nullptr) {
-#pragma unroll
-              for (int k = 0; k < V; ++k) v[k] = act_fwd(fmaf(v[k], isc[k], ish[k]), xf.act);
-            }
-#pragma unroll
-            for (int pp = 0; pp < P; ++pp) {
-              const int kx = ix - pp * S;
-              if (kx >= 0 && kx < K) {
-#pragma unroll
-                for (int k = 0; k < V; ++k) acc[kx][k] = fmaf(g[pp][k], v[k], acc[kx][k]);
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < K; ++q)
-#pragma unroll
-          for (int k = 0; k < V; ++k) atomicAdd(&smem[(ky * K + q) * C + c0 + k], acc[q][k]);
-      }
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < KK * C; i += kThreads) {
-    const int q = i / C, c = i % C;
-    atomicAdd(dw + (size_t)c * KK + q, smem[i]);
-  }
-}
-
 // Shared-memory tiled depthwise weight gradient (same contract as dw_wgrad_kernel).  A CTA stages the transformed
 // input tile and the dz tile of one sample / 32-channel chunk in shared memory (BatchNorm+activation applied once
 // per input element), keeps all K*K tap accumulators of its channel slice in registers across its tiles, and

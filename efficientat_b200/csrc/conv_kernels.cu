@@ -630,6 +630,24 @@ int launch_dw(const T* in, const float* wt, T* out, int B, int F, int Tn, int C,
   if (C % V != 0) { eat_set_error("dw conv: channels must be a multiple of the vector width"); return EAT_ERR_ARG; }
   const int pad = (k - 1) / 2;
   const int Fo = (F + 2 * pad - k) / stride + 1, To = (Tn + 2 * pad - k) / stride + 1;
+  if (k == 3 || k == 5) {
+    const bool tiled = (k == 5);     // measured (profiles/r01_dw_microbench*): smem tiling pays for 5x5, not for 3x3
+    if (!tiled) {
+      const int cv = C / V;
+      const int ppb = kThreads / cv > 0 ? kThreads / cv : 1;
+      const int units = Fo * ceil_div(To, (stride == 1 && V == 4) ? 8 : 4);
+      int gx = ceil_div(units, ppb);
+      const int cap = max(1, (148 * 8) / max(B, 1));
+      if (gx > cap) gx = cap;
+      dim3 grid(gx, B);
+      size_t smem = 2 * (size_t)C * sizeof(float);
+      if (stride == 1) dw_kernel<T, 3, 1><<<grid, kThreads, smem, st>>>(in, wt, out, F, Tn, Fo, To, C, xf, scale, shift, act, res, flip, pool, ssum, ssq, dy);
+      else if (stride == 2) dw_kernel<T, 3, 2><<<grid, kThreads, smem, st>>>(in, wt, out, F, Tn, Fo, To, C, xf, scale, shift, act, res, flip, pool, ssum, ssq, dy);
+      else { eat_set_error("dw conv: stride must be 1 or 2"); return EAT_ERR_UNSUPPORTED; }
+      EAT_CHECK_LAUNCH();
+      return EAT_OK;
+    }
+  }
   // shared-memory tiled kernel: grid.x = channel chunks x tile groups (each CTA strides over its group's tiles)
   const int FR = stride == 1 ? 8 : 4, TT = stride == 1 ? 32 : 16;
   const int IR = (FR - 1) * stride + k, IT = (TT - 1) * stride + k;

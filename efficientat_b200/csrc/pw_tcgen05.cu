@@ -57,8 +57,9 @@ struct TcParams {
 };
 
 // first row / row limit / sample of M tile `mt`
+template <bool DYN>
 __device__ __forceinline__ void tile_rows(const TcParams& p, int mt, long long& m0, long long& m_lim, int& b) {
-  if (p.tps == 0) { m0 = (long long)mt * BM; m_lim = p.M; b = 0; return; }
+  if (!DYN) { m0 = (long long)mt * BM; m_lim = p.M; b = 0; return; }
   b = mt / p.tps;
   const int j = mt - b * p.tps;
   m0 = (long long)b * p.tile_rps + (long long)j * BM;
@@ -109,13 +110,12 @@ template <> struct OutVec<__nv_bfloat16> {
 __device__ __forceinline__ float act_sel(float v, int act) {     // branch-free activation
   const float r = fmaxf(v, 0.f);
   const float h = v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
-  if (act == EAT_ACT_SIGMOID) return 1.f / (1.f + expf(-v));      // rare (DyMN context nets): uniform branch
   return act == EAT_ACT_HSWISH ? h : (act == EAT_ACT_RELU ? r : v);
 }
 
 // T: activation storage type.  NP = 1: operands rounded to bf16 (bf16 mode); NP = 2: hi/lo split (fp32 mode).
-template <typename T, int NP, int STAGES, int BN_MAX>
-__global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
+template <typename T, int NP, int STAGES, int BN_MAX, bool DYN>
+__global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {  // 17 warps are allocated as 20: 96 registers/thread is the ceiling
   constexpr int B_TILE_BYTES = BN_MAX * 128;
   constexpr int STAGE_BYTES = NP * (A_TILE_BYTES + B_TILE_BYTES);
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -160,9 +160,9 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
       const int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;       // m fastest: a CTA stays on one N tile
       long long m0, m_lim;
       int bsample;
-      tile_rows(p, mt, m0, m_lim, bsample);
+      tile_rows<DYN>(p, mt, m0, m_lim, bsample);
       float datt[4] = {0.f, 0.f, 0.f, 0.f};
-      if (p.dyn_att != nullptr) {
+      if (DYN) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) datt[j] = j < p.dyn_k ? __ldg(p.dyn_att + (size_t)bsample * p.dyn_k + j) : 0.f;
       }
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
             const int r = rb + i * rstep;
             const int n = n0 + r;
             if (kok && r < BN && n < N) {
-              if (p.dyn_att == nullptr) load_chunk<float>(p.W + (size_t)n * K + k, wv[i]);
+              if (!DYN) load_chunk<float>(p.W + (size_t)n * K + k, wv[i]);
               else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) wv[i][j] = 0.f;
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
       const int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;
       long long m0, m_lim;
       int bsample;
-      tile_rows(p, mt, m0, m_lim, bsample);
+      tile_rows<DYN>(p, mt, m0, m_lim, bsample);
       const int n0 = nt * BN;
       if (nt != cur_nt) {
         // new N tile: flush the previous tile's statistics, stage this tile's epilogue affine
@@ -433,13 +433,13 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
   }
 }
 
-template <typename T, int NP, int STAGES, int BN_MAX>
+template <typename T, int NP, int STAGES, int BN_MAX, bool DYN>
 int launch_tc(const TcParams& p0, cudaStream_t st) {
   TcParams p = p0;
   p.n_tiles = ceil_div(p.N, BN_MAX);
   p.BN = ceil_div(ceil_div(p.N, p.n_tiles), 16) * 16;
   p.n_tiles = ceil_div(p.N, p.BN);
-  if (p.dyn_att != nullptr) {
+  if (DYN) {
     p.tps = ceil_div(p.tile_rps, BM);
     p.m_tiles = (p.M / p.tile_rps) * p.tps;
   } else {
@@ -453,7 +453,7 @@ int launch_tc(const TcParams& p0, cudaStream_t st) {
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(pw_tc_kernel<T, NP, STAGES, BN_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(pw_tc_kernel<T, NP, STAGES, BN_MAX, DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { eat_set_error(cudaGetErrorString(e)); return EAT_ERR_CUDA; }
     attr_done = true;
   }
@@ -462,7 +462,7 @@ int launch_tc(const TcParams& p0, cudaStream_t st) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < sms ? tiles : sms;
-  pw_tc_kernel<T, NP, STAGES, BN_MAX><<<grid, kThreads, smem, st>>>(p);
+  pw_tc_kernel<T, NP, STAGES, BN_MAX, DYN><<<grid, kThreads, smem, st>>>(p);
   EAT_CHECK_LAUNCH();
   return EAT_OK;
 }
@@ -474,6 +474,7 @@ extern "C" int eat_pw_tc_fwd(const void* A, int a_dtype, const float* W, int w_t
                              int rows_per_sample, const float* scale, const float* shift, int act, const void* residual,
                              double* stat_sum, double* stat_sq, cudaStream_t st) {
   if (M == 0) return EAT_OK;
+  if (act == EAT_ACT_SIGMOID || in_act == EAT_ACT_SIGMOID) { eat_set_error("pw_tc: sigmoid epilogues run on the CUDA-core GEMM (eat_gemm_simt_fwd)"); return EAT_ERR_UNSUPPORTED; }
   if (w_trans) { eat_set_error("pw_tc: transposed weights are not supported (pre-transpose with eat_transpose_f32)"); return EAT_ERR_UNSUPPORTED; }
   if (a_dtype != c_dtype) { eat_set_error("pw_tc: A and C must share the storage dtype"); return EAT_ERR_UNSUPPORTED; }
   if (K % 8 != 0 || N % 8 != 0) { eat_set_error("pw_tc: K and N must be multiples of 8"); return EAT_ERR_ARG; }
@@ -484,8 +485,8 @@ extern "C" int eat_pw_tc_fwd(const void* A, int a_dtype, const float* W, int w_t
   p.xf = InXform{in_scale, in_shift, gate, in_act, rows_per_sample > 0 ? rows_per_sample : 1};
   p.scale = scale; p.shift = shift; p.act = act; p.stat_sum = stat_sum; p.stat_sq = stat_sq;
   p.dyn_att = nullptr; p.dyn_k = 0; p.tps = 0; p.tile_rps = 0;
-  if (a_dtype == EAT_BF16) return launch_tc<__nv_bfloat16, 1, 3, 256>(p, st);
-  return launch_tc<float, 2, 2, 128>(p, st);
+  if (a_dtype == EAT_BF16) return launch_tc<__nv_bfloat16, 1, 3, 256, false>(p, st);
+  return launch_tc<float, 2, 2, 128, false>(p, st);
 }
 
 // DynamicConv 1x1 (reference models/dymn/dy_block.py:103-131): W holds dyn_k kernels [dyn_k][N][K]; sample b uses
@@ -504,8 +505,8 @@ extern "C" int eat_pw_tc_dyn_fwd(const void* A, int dtype, const float* W, const
   p.xf = InXform{in_scale, in_shift, nullptr, in_act, rows_per_sample};
   p.scale = scale; p.shift = shift; p.act = act; p.stat_sum = stat_sum; p.stat_sq = stat_sq;
   p.dyn_att = att; p.dyn_k = dyn_k; p.tile_rps = rows_per_sample; p.tps = 1;
-  if (dtype == EAT_BF16) return launch_tc<__nv_bfloat16, 1, 3, 256>(p, st);
-  return launch_tc<float, 2, 2, 128>(p, st);
+  if (dtype == EAT_BF16) return launch_tc<__nv_bfloat16, 1, 3, 256, true>(p, st);
+  return launch_tc<float, 2, 2, 128, true>(p, st);
 }
 
 // [R, Cc] fp32 -> [Cc, R]  (weights for the data-gradient GEMM)

@@ -106,7 +106,7 @@ class MNEngine:
                 _ptr(stats[0]) if stats is not None else 0, _ptr(stats[1]) if stats is not None else 0, _stream())
         L = lib()
         use_tc = (self.gemm_impl != "simt" and a_code == c_code and M >= self.tc_min_rows and K % 8 == 0
-                  and N % 8 == 0)
+                  and N % 8 == 0 and act != 3 and in_act != 3)      # sigmoid epilogues (DyMN context nets) stay on CUDA cores
         if use_tc:
             if w_trans:      # data gradient: feed W^T [N, K] as a K-major operand
                 wt = torch.empty(N, K, device=w.device, dtype=torch.float32)
