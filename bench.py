@@ -162,11 +162,11 @@ def algo_bytes(name, a):
         dt, B, P, C = a[12:16]
         return B * P * C * sz(dt) * (3 if gA else 2)
     if name == "eat_dw_conv_dgrad":
-        dz, wt, res, din, dt, B, F, T, C, k, s = a[:11]
+        dz, wt, wbs, res, din, dt, B, F, T, C, k, s = a[:12]
         Fo, To = (F + 2 * ((k - 1) // 2) - k) // s + 1, (T + 2 * ((k - 1) // 2) - k) // s + 1
         return B * C * sz(dt) * (F * T * (2 if res else 1) + Fo * To)
     if name == "eat_dw_conv_wgrad":
-        dz, inp, s0, s1, act, dw, dt, B, F, T, C, k, s = a[:13]
+        dz, inp, s0, s1, act, dw, dbs, dt, B, F, T, C, k, s = a[:14]
         Fo, To = (F + 2 * ((k - 1) // 2) - k) // s + 1, (T + 2 * ((k - 1) // 2) - k) // s + 1
         return B * C * sz(dt) * (F * T + Fo * To)
     if name == "eat_mel_fwd":

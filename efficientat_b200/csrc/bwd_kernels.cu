@@ -187,11 +187,12 @@ __global__ void __launch_bounds__(kThreads) se_fc_bwd_kernel(const float* __rest
 template <typename T, int K, int S>
 __global__ void __launch_bounds__(kThreads) dw_dgrad_kernel(const T* __restrict__ dz, const float* __restrict__ wt,
                                                             const T* __restrict__ res, T* __restrict__ din,
-                                                            int F, int Tn, int Fo, int To, int C) {
+                                                            int F, int Tn, int Fo, int To, int C, long long wt_bstride) {
   constexpr int V = Vec<T>::N;
   constexpr int PAD = (K - 1) / 2;
   const int cv = C / V;
   const int b = blockIdx.y;
+  wt += (size_t)b * wt_bstride;
   const long long nvec = (long long)F * Tn * cv;
   const T* dzb = dz + (size_t)b * Fo * To * C;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += (long long)gridDim.x * kThreads) {
@@ -451,7 +452,8 @@ int launch_bn_bwd_reduce(const void* gA, const float* gate, const float* dpool, 
 
 template <typename T>
 int launch_dw_bwd(int which, const void* dz, const float* wt, const void* in, InXform xf, const void* res, void* din,
-                  float* dw, int B, int F, int Tn, int C, int k, int stride, cudaStream_t st) {
+                  float* dw, int B, int F, int Tn, int C, int k, int stride, cudaStream_t st, long long wt_bstride = 0,
+                  long long dw_bstride = 0) {
   constexpr int V = Vec<T>::N;
   if (C % V != 0) { eat_set_error("dw bwd: channels must be a multiple of the vector width"); return EAT_ERR_ARG; }
   const int pad = (k - 1) / 2;
@@ -461,7 +463,7 @@ int launch_dw_bwd(int which, const void* dz, const float* wt, const void* in, In
     long long nvec = (long long)F * Tn * cv;
     int gx = (int)min((long long)max(1, (148 * 16) / max(B, 1)), ceil_div_ll(nvec, kThreads));
     dim3 grid(gx < 1 ? 1 : gx, B);
-#define EAT_DG(KK, SS) dw_dgrad_kernel<T, KK, SS><<<grid, kThreads, 0, st>>>((const T*)dz, wt, (const T*)res, (T*)din, F, Tn, Fo, To, C)
+#define EAT_DG(KK, SS) dw_dgrad_kernel<T, KK, SS><<<grid, kThreads, 0, st>>>((const T*)dz, wt, (const T*)res, (T*)din, F, Tn, Fo, To, C, wt_bstride)
     if (k == 3 && stride == 1) EAT_DG(3, 1); else if (k == 3 && stride == 2) EAT_DG(3, 2);
     else if (k == 5 && stride == 1) EAT_DG(5, 1); else if (k == 5 && stride == 2) EAT_DG(5, 2);
     else { eat_set_error("dw dgrad: only k in {3,5}, stride in {1,2}"); return EAT_ERR_UNSUPPORTED; }
@@ -479,7 +481,7 @@ int launch_dw_bwd(int which, const void* dz, const float* wt, const void* in, In
   do {                                                                                                          \
     static bool attr = false;                                                                                   \
     if (!attr) { cudaFuncSetAttribute(dw_wgrad_tile_kernel<T, KK, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); attr = true; } \
-    dw_wgrad_tile_kernel<T, KK, SS><<<grid, kThreads, smem, st>>>((const T*)dz, (const T*)in, xf, dw, F, Tn, Fo, To, C, 0); \
+    dw_wgrad_tile_kernel<T, KK, SS><<<grid, kThreads, smem, st>>>((const T*)dz, (const T*)in, xf, dw, F, Tn, Fo, To, C, dw_bstride); \
   } while (0)
     if (k == 3 && stride == 1) EAT_WG(3, 1); else if (k == 3 && stride == 2) EAT_WG(3, 2);
     else if (k == 5 && stride == 1) EAT_WG(5, 1); else if (k == 5 && stride == 2) EAT_WG(5, 2);
@@ -552,24 +554,25 @@ int eat_se_fc_bwd(const float* dgate, const float* gate, const float* hidden, co
   return EAT_OK;
 }
 
-extern "C" int eat_dw_conv_dgrad_s1(const void* dz, const float* wt, const void* res, void* din, int dtype, int B,
-                                    int F, int T, int C, int k, cudaStream_t st);
+extern "C" int eat_dw_conv_dgrad_s1(const void* dz, const float* wt, long long wt_bstride, const void* res, void* din,
+                                    int dtype, int B, int F, int T, int C, int k, cudaStream_t st);
 
-int eat_dw_conv_dgrad(const void* dz, const float* wt, const void* res, void* din, int dtype, int B, int F, int T,
-                      int C, int k, int stride, cudaStream_t st) {
+int eat_dw_conv_dgrad(const void* dz, const float* wt, long long wt_bstride, const void* res, void* din, int dtype, int B,
+                      int F, int T, int C, int k, int stride, cudaStream_t st) {
   if (B == 0) return EAT_OK;
-  if (stride == 1 && (k == 3 || k == 5)) return eat_dw_conv_dgrad_s1(dz, wt, res, din, dtype, B, F, T, C, k, st);
+  if (stride == 1 && (k == 3 || k == 5)) return eat_dw_conv_dgrad_s1(dz, wt, wt_bstride, res, din, dtype, B, F, T, C, k, st);
   InXform xf{nullptr, nullptr, nullptr, 0, 0};
-  if (dtype == EAT_BF16) return launch_dw_bwd<__nv_bfloat16>(0, dz, wt, nullptr, xf, res, din, nullptr, B, F, T, C, k, stride, st);
-  return launch_dw_bwd<float>(0, dz, wt, nullptr, xf, res, din, nullptr, B, F, T, C, k, stride, st);
+  if (dtype == EAT_BF16) return launch_dw_bwd<__nv_bfloat16>(0, dz, wt, nullptr, xf, res, din, nullptr, B, F, T, C, k, stride, st, wt_bstride);
+  return launch_dw_bwd<float>(0, dz, wt, nullptr, xf, res, din, nullptr, B, F, T, C, k, stride, st, wt_bstride);
 }
 
 int eat_dw_conv_wgrad(const void* dz, const void* in, const float* in_scale, const float* in_shift, int in_act,
-                      float* dw, int dtype, int B, int F, int T, int C, int k, int stride, cudaStream_t st) {
+                      float* dw, long long dw_bstride, int dtype, int B, int F, int T, int C, int k, int stride,
+                      cudaStream_t st) {
   if (B == 0) return EAT_OK;
   InXform xf{in_scale, in_shift, nullptr, in_act, 0};
-  if (dtype == EAT_BF16) return launch_dw_bwd<__nv_bfloat16>(1, dz, nullptr, in, xf, nullptr, nullptr, dw, B, F, T, C, k, stride, st);
-  return launch_dw_bwd<float>(1, dz, nullptr, in, xf, nullptr, nullptr, dw, B, F, T, C, k, stride, st);
+  if (dtype == EAT_BF16) return launch_dw_bwd<__nv_bfloat16>(1, dz, nullptr, in, xf, nullptr, nullptr, dw, B, F, T, C, k, stride, st, 0, dw_bstride);
+  return launch_dw_bwd<float>(1, dz, nullptr, in, xf, nullptr, nullptr, dw, B, F, T, C, k, stride, st, 0, dw_bstride);
 }
 
 int eat_stem_wgrad(const void* dz, int dtype, const float* x, float* dw, int B, int F, int T, int C, int stride,

@@ -729,13 +729,14 @@ int eat_dw_conv_fwd_dy(const void* in, const float* wt, long long wt_bstride, vo
 }
 
 // stride-1 depthwise data gradient = the forward kernel with mirrored taps (+ residual-gradient add)
-int eat_dw_conv_dgrad_s1(const void* dz, const float* wt, const void* res, void* din, int dtype, int B, int F, int T,
-                         int C, int k, cudaStream_t st) {
+int eat_dw_conv_dgrad_s1(const void* dz, const float* wt, long long wt_bstride, const void* res, void* din, int dtype,
+                         int B, int F, int T, int C, int k, cudaStream_t st) {
   if (B == 0) return EAT_OK;
   InXform xf{nullptr, nullptr, nullptr, 0, 0};
+  DyEpi dy{nullptr, nullptr, nullptr, nullptr, nullptr, wt_bstride};
   if (dtype == EAT_BF16)
-    return launch_dw<__nv_bfloat16>((const __nv_bfloat16*)dz, wt, (__nv_bfloat16*)din, B, F, T, C, k, 1, xf, nullptr, nullptr, 0, (const __nv_bfloat16*)res, 1, nullptr, nullptr, nullptr, st);
-  return launch_dw<float>((const float*)dz, wt, (float*)din, B, F, T, C, k, 1, xf, nullptr, nullptr, 0, (const float*)res, 1, nullptr, nullptr, nullptr, st);
+    return launch_dw<__nv_bfloat16>((const __nv_bfloat16*)dz, wt, (__nv_bfloat16*)din, B, F, T, C, k, 1, xf, nullptr, nullptr, 0, (const __nv_bfloat16*)res, 1, nullptr, nullptr, nullptr, st, dy);
+  return launch_dw<float>((const float*)dz, wt, (float*)din, B, F, T, C, k, 1, xf, nullptr, nullptr, 0, (const float*)res, 1, nullptr, nullptr, nullptr, st, dy);
 }
 
 int eat_bn_fold(const float* gamma, const float* beta, const float* rmean, const float* rvar, float eps,

@@ -32,6 +32,8 @@ struct WgParams {
   InXform xf;
   int KT;                 // dW columns per CTA (multiple of 16, <= KT_MAX)
   int n_tiles, k_tiles, rows_per_split;
+  int sample_rows;        // > 0: per-sample gradients dW[b] (DynamicConv); splits never straddle samples
+  int splits_per_sample;
 };
 
 // MN-major SWIZZLE_128B descriptor: LBO between 64-element atoms along MN, SBO between 8-row groups along K
@@ -84,9 +86,19 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(WgParams p) {
   const int ot = blockIdx.x % tiles, split = blockIdx.x / tiles;
   const int nt = ot / p.k_tiles, kt = ot - nt * p.k_tiles;
   const int n0 = nt * WM, k0 = kt * p.KT;
-  const long long m_begin = (long long)split * p.rows_per_split;
-  long long m_end = m_begin + p.rows_per_split;
-  if (m_end > p.M) m_end = p.M;
+  long long m_begin, m_end;
+  float* __restrict__ dWout = p.dW;
+  if (p.sample_rows > 0) {
+    const int b = split / p.splits_per_sample, j = split - b * p.splits_per_sample;
+    m_begin = (long long)b * p.sample_rows + (long long)j * p.rows_per_split;
+    m_end = m_begin + p.rows_per_split;
+    if (m_end > (long long)(b + 1) * p.sample_rows) m_end = (long long)(b + 1) * p.sample_rows;
+    dWout += (size_t)b * p.N * p.K;
+  } else {
+    m_begin = (long long)split * p.rows_per_split;
+    m_end = m_begin + p.rows_per_split;
+    if (m_end > p.M) m_end = p.M;
+  }
   const int n_blocks = (int)((m_end - m_begin + MB - 1) / MB);
   const int N = p.N, K = p.K;
   const int ncG = (min(WM, N - n0) + 7) >> 3;            // valid 16-byte chunks per G row
@@ -238,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(WgParams p) {
             const int n = n0 + q * 32 + row;
             if (n < N) {
               const float4 v = *reinterpret_cast<const float4*>(stg + row * STG_LD + col4);
-              atomicAdd(reinterpret_cast<float4*>(p.dW + (size_t)n * K + k), v);
+              atomicAdd(reinterpret_cast<float4*>(dWout + (size_t)n * K + k), v);
             }
           }
         }
@@ -265,12 +277,25 @@ int launch_wg(const WgParams& p0, cudaStream_t st) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = p.n_tiles * p.k_tiles;
-  int splits = max(1, (2 * sms) / tiles);
-  long long rows = ceil_div_ll(p.M, splits);
-  rows = ceil_div_ll(rows, MB) * MB;
-  if (rows < 4 * MB) rows = 4 * MB;
-  splits = (int)ceil_div_ll(p.M, rows);
-  p.rows_per_split = (int)rows;
+  int splits;
+  if (p.sample_rows > 0) {
+    const int B = p.M / p.sample_rows;
+    int sps = max(1, (2 * sms) / max(1, tiles * B));
+    long long rows = ceil_div_ll(p.sample_rows, sps);
+    rows = ceil_div_ll(rows, MB) * MB;
+    sps = (int)ceil_div_ll(p.sample_rows, rows);
+    p.rows_per_split = (int)rows;
+    p.splits_per_sample = sps;
+    splits = sps * B;
+  } else {
+    splits = max(1, (2 * sms) / tiles);
+    long long rows = ceil_div_ll(p.M, splits);
+    rows = ceil_div_ll(rows, MB) * MB;
+    if (rows < 4 * MB) rows = 4 * MB;
+    splits = (int)ceil_div_ll(p.M, rows);
+    p.rows_per_split = (int)rows;
+    p.splits_per_sample = 0;
+  }
   constexpr size_t smem = (size_t)STAGES * NP * (MB * G_ATOMS * 128 + MB * (KT_MAX / 64) * 128) +
                           4 * 32 * STG_LD * sizeof(float) + (2 * STAGES + 1) * sizeof(uint64_t) + 16;
   static_assert(smem <= 227 * 1024, "shared memory budget");
@@ -300,6 +325,23 @@ extern "C" int eat_pw_tc_wgrad(const void* G, int g_dtype, const void* A, int a_
   WgParams p;
   p.G = G; p.A = A; p.dW = dW; p.M = (int)M; p.N = N; p.K = K;
   p.xf = InXform{in_scale, in_shift, gate, in_act, rows_per_sample > 0 ? rows_per_sample : 1};
+  p.sample_rows = 0;
   if (a_dtype == EAT_BF16) return launch_wg<__nv_bfloat16, 1, 4, 256>(p, st);
+  return launch_wg<float, 2, 2, 256>(p, st);
+}
+
+// Per-sample weight gradients S[b] = G_b^T . A_b  (S: [B, N, K] fp32, zeroed by the caller); the DynamicConv bank and
+// attention gradients follow from S with eat_dyn_wgrad_mix (reference models/dymn/dy_block.py:103-131 backward).
+extern "C" int eat_pw_tc_wgrad_persample(const void* G, const void* A, int dtype, float* S, long long M, int N, int K,
+                                         int rows_per_sample, cudaStream_t st) {
+  if (M == 0) return EAT_OK;
+  if (K % 8 != 0 || N % 8 != 0) { eat_set_error("pw_tc_wgrad_persample: K and N must be multiples of 8"); return EAT_ERR_ARG; }
+  if (rows_per_sample < 1 || M % rows_per_sample != 0) { eat_set_error("pw_tc_wgrad_persample: M must be B * rows_per_sample"); return EAT_ERR_ARG; }
+  if (M >= (1ll << 31) - MB) { eat_set_error("pw_tc_wgrad_persample: M too large"); return EAT_ERR_ARG; }
+  WgParams p;
+  p.G = G; p.A = A; p.dW = S; p.M = (int)M; p.N = N; p.K = K;
+  p.xf = InXform{nullptr, nullptr, nullptr, 0, rows_per_sample};
+  p.sample_rows = rows_per_sample;
+  if (dtype == EAT_BF16) return launch_wg<__nv_bfloat16, 1, 4, 256>(p, st);
   return launch_wg<float, 2, 2, 256>(p, st);
 }

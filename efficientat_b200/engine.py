@@ -277,51 +277,68 @@ class MNEngine:
         L.bn_apply(z0.data_ptr(), sc0[0].data_ptr(), sc0[1].data_ptr(), HS, 0, a.data_ptr(), dc, B * Fi * Ti, c0, st)
         S["stem"] = dict(z=z0, sc=sc0, sv=sv0, Fo=Fi, To=Ti)
         for blk in self.blocks:
-            R = {"inp": a, "Fi": Fi, "Ti": Ti}
-            inp = a
-            M = B * Fi * Ti
-            if blk.expand is not None:
-                z1 = torch.empty(B, Fi, Ti, blk.cexp, device=dev, dtype=td)
-                stt = self._new_stats(blk.cexp, dev)
-                self._gemm(inp, blk.expand[0].weight, z1, M, blk.cexp, blk.cin, stats=stt)
-                sc1, sv1 = self._finalize(blk.expand[1], stt, M, dev)
-                R.update(z1=z1, sc1=sc1, sv1=sv1)
-                dw_in, dw_sc = z1, sc1
-            else:
-                dw_in, dw_sc = inp, None
-            Fo, To = _conv_out(Fi, blk.k, blk.stride), _conv_out(Ti, blk.k, blk.stride)
-            Mo = B * Fo * To
-            z2 = torch.empty(B, Fo, To, blk.cexp, device=dev, dtype=td)
-            stt = self._new_stats(blk.cexp, dev)
-            wt = self._dw_weights(blk.dw[0], dev)
-            L.dw_conv_fwd(dw_in.data_ptr(), wt.data_ptr(), z2.data_ptr(), dc, B, Fi, Ti, blk.cexp, blk.k, blk.stride,
-                          _ptr(dw_sc[0]) if dw_sc is not None else 0, _ptr(dw_sc[1]) if dw_sc is not None else 0,
-                          blk.act if dw_sc is not None else 0, 0, 0, 0, 0, stt[0].data_ptr(), stt[1].data_ptr(), st)
-            sc2, sv2 = self._finalize(blk.dw[1], stt, Mo, dev)
-            R.update(z2=z2, sc2=sc2, sv2=sv2, wt=wt, Fo=Fo, To=To)
-            gate = None
-            if blk.se is not None:
-                Sq = blk.se.fc1.out_features
-                pool = torch.zeros(B, blk.cexp, device=dev, dtype=torch.float32)
-                L.bn_act_pool(z2.data_ptr(), sc2[0].data_ptr(), sc2[1].data_ptr(), blk.act, pool.data_ptr(),
-                              1.0 / (Fo * To), dc, B, Fo * To, blk.cexp, st)
-                gate = torch.empty(B, blk.cexp, device=dev, dtype=torch.float32)
-                hidden = torch.empty(B, Sq, device=dev, dtype=torch.float32)
-                L.se_fc_fwd(pool.data_ptr(), 1.0, blk.se.fc1.weight.data_ptr(), blk.se.fc1.bias.data_ptr(),
-                            blk.se.fc2.weight.data_ptr(), blk.se.fc2.bias.data_ptr(), gate.data_ptr(),
-                            hidden.data_ptr(), B, blk.cexp, Sq, st)
-                R.update(mean=pool, gate=gate, hidden=hidden)
-            z3 = torch.empty(B, Fo, To, blk.cout, device=dev, dtype=td)
-            stt = self._new_stats(blk.cout, dev)
-            self._gemm(z2, blk.proj[0].weight, z3, Mo, blk.cout, blk.cexp, in_sc=sc2, in_act=blk.act, gate=gate,
-                       rows_per_sample=Fo * To, stats=stt)
-            sc3, sv3 = self._finalize(blk.proj[1], stt, Mo, dev)
-            a = torch.empty(B, Fo, To, blk.cout, device=dev, dtype=td)
-            L.bn_apply(z3.data_ptr(), sc3[0].data_ptr(), sc3[1].data_ptr(), 0, _ptr(inp) if blk.res else 0,
-                       a.data_ptr(), dc, Mo, blk.cout, st)
-            R.update(z3=z3, sc3=sc3, sv3=sv3)
+            a, Fi, Ti, R = self._block_train_fwd(blk, a, B, Fi, Ti)
             S["blocks"].append(R)
-            Fi, Ti = Fo, To
+        logits, feat = self._head_train_fwd(a, B, Fi, Ti, S, dropout_mask)
+        return logits, feat, S
+
+    def _block_train_fwd(self, blk, a, B, Fi, Ti):
+        return self._ir_block_train_fwd(blk, a, B, Fi, Ti)
+
+    def _ir_block_train_fwd(self, blk, a, B, Fi, Ti):
+        L = lib()
+        dev, st = a.device, _stream()
+        td, dc = self.tdtype, self.dcode
+        R = {"inp": a, "Fi": Fi, "Ti": Ti}
+        inp = a
+        M = B * Fi * Ti
+        if blk.expand is not None:
+            z1 = torch.empty(B, Fi, Ti, blk.cexp, device=dev, dtype=td)
+            stt = self._new_stats(blk.cexp, dev)
+            self._gemm(inp, blk.expand[0].weight, z1, M, blk.cexp, blk.cin, stats=stt)
+            sc1, sv1 = self._finalize(blk.expand[1], stt, M, dev)
+            R.update(z1=z1, sc1=sc1, sv1=sv1)
+            dw_in, dw_sc = z1, sc1
+        else:
+            dw_in, dw_sc = inp, None
+        Fo, To = _conv_out(Fi, blk.k, blk.stride), _conv_out(Ti, blk.k, blk.stride)
+        Mo = B * Fo * To
+        z2 = torch.empty(B, Fo, To, blk.cexp, device=dev, dtype=td)
+        stt = self._new_stats(blk.cexp, dev)
+        wt = self._dw_weights(blk.dw[0], dev)
+        L.dw_conv_fwd(dw_in.data_ptr(), wt.data_ptr(), z2.data_ptr(), dc, B, Fi, Ti, blk.cexp, blk.k, blk.stride,
+                      _ptr(dw_sc[0]) if dw_sc is not None else 0, _ptr(dw_sc[1]) if dw_sc is not None else 0,
+                      blk.act if dw_sc is not None else 0, 0, 0, 0, 0, stt[0].data_ptr(), stt[1].data_ptr(), st)
+        sc2, sv2 = self._finalize(blk.dw[1], stt, Mo, dev)
+        R.update(z2=z2, sc2=sc2, sv2=sv2, wt=wt, Fo=Fo, To=To)
+        gate = None
+        if blk.se is not None:
+            Sq = blk.se.fc1.out_features
+            pool = torch.zeros(B, blk.cexp, device=dev, dtype=torch.float32)
+            L.bn_act_pool(z2.data_ptr(), sc2[0].data_ptr(), sc2[1].data_ptr(), blk.act, pool.data_ptr(),
+                          1.0 / (Fo * To), dc, B, Fo * To, blk.cexp, st)
+            gate = torch.empty(B, blk.cexp, device=dev, dtype=torch.float32)
+            hidden = torch.empty(B, Sq, device=dev, dtype=torch.float32)
+            L.se_fc_fwd(pool.data_ptr(), 1.0, blk.se.fc1.weight.data_ptr(), blk.se.fc1.bias.data_ptr(),
+                        blk.se.fc2.weight.data_ptr(), blk.se.fc2.bias.data_ptr(), gate.data_ptr(),
+                        hidden.data_ptr(), B, blk.cexp, Sq, st)
+            R.update(mean=pool, gate=gate, hidden=hidden)
+        z3 = torch.empty(B, Fo, To, blk.cout, device=dev, dtype=td)
+        stt = self._new_stats(blk.cout, dev)
+        self._gemm(z2, blk.proj[0].weight, z3, Mo, blk.cout, blk.cexp, in_sc=sc2, in_act=blk.act, gate=gate,
+                   rows_per_sample=Fo * To, stats=stt)
+        sc3, sv3 = self._finalize(blk.proj[1], stt, Mo, dev)
+        a = torch.empty(B, Fo, To, blk.cout, device=dev, dtype=td)
+        L.bn_apply(z3.data_ptr(), sc3[0].data_ptr(), sc3[1].data_ptr(), 0, _ptr(inp) if blk.res else 0,
+                   a.data_ptr(), dc, Mo, blk.cout, st)
+        R.update(z3=z3, sc3=sc3, sv3=sv3)
+        return a, Fo, To, R
+
+    def _head_train_fwd(self, a, B, Fi, Ti, S, dropout_mask):
+        L = lib()
+        dev, st = a.device, _stream()
+        td, dc = self.tdtype, self.dcode
+        HS = ACT["hswish"]
         conv, bn = self.last[0], self.last[1]
         cl = conv.out_channels
         M = B * Fi * Ti
@@ -346,7 +363,7 @@ class MNEngine:
         self._gemm(h_pre, self.fc2.weight, logits, B, self.fc2.out_features, n1, in_sc=ident, in_act=HS,
                    gate=dropout_mask, rows_per_sample=1, bias=self.fc2.bias, a_code=0, c_code=0)
         S["head"] = dict(feat=feat, h_pre=h_pre, mask=dropout_mask, ident=ident)
-        return logits, feat, S
+        return logits, feat
 
     def _ident(self, n, dev):
         t = torch.empty(2, n, device=dev, dtype=torch.float32)
@@ -372,21 +389,80 @@ class MNEngine:
         else:
             lib().gemm_simt_wgrad(*args)
 
-    def _bn_bwd(self, gA, gate, dpool, z, sc, sv, act, B, P, C, dgamma, dbeta, dev):
+    def _bn_bwd(self, gA, gate, dpool, z, sc, sv, act, B, P, C, dgamma, dbeta, dev, code=None):
         """two-pass BatchNorm(+activation) backward -> dz (same dtype/shape as z)."""
         L = lib()
         st = _stream()
+        code = self.dcode if code is None else code
         s = torch.zeros(2, C, device=dev, dtype=torch.float64)
         L.bn_bwd_reduce(_ptr(gA), _ptr(gate), _ptr(dpool), z.data_ptr(), sc[0].data_ptr(), sc[1].data_ptr(),
-                        sv[0].data_ptr(), sv[1].data_ptr(), act, self.dcode, B, P, C, s[0].data_ptr(), s[1].data_ptr(), st)
+                        sv[0].data_ptr(), sv[1].data_ptr(), act, code, B, P, C, s[0].data_ptr(), s[1].data_ptr(), st)
         coef = torch.empty(2, C, device=dev, dtype=torch.float32)
         L.bn_bwd_finalize(s[0].data_ptr(), s[1].data_ptr(), float(B * P), _ptr(dgamma), _ptr(dbeta),
                           coef[0].data_ptr(), coef[1].data_ptr(), C, st)
         dz = torch.empty_like(z)
         L.bn_bwd_apply(_ptr(gA), _ptr(gate), _ptr(dpool), z.data_ptr(), sc[0].data_ptr(), sc[1].data_ptr(),
                        sv[0].data_ptr(), sv[1].data_ptr(), act, coef[0].data_ptr(), coef[1].data_ptr(), dz.data_ptr(),
-                       self.dcode, B, P, C, st)
+                       code, B, P, C, st)
         return dz
+
+    def _block_bwd(self, blk, R, dy, G, B):
+        return self._ir_block_bwd(blk, R, dy, G, B)
+
+    def _ir_block_bwd(self, blk, R, dy, G, B):
+        """backward of one InvertedResidual; returns the gradient w.r.t. the block input"""
+        L = lib()
+        st = _stream()
+        dev = dy.device
+        td, dc = self.tdtype, self.dcode
+        Fi, Ti, Fo, To = R["Fi"], R["Ti"], R["Fo"], R["To"]
+        Pi, Po = Fi * Ti, Fo * To
+        gate = R.get("gate")
+        # project: BN3 (no activation)
+        dz3 = self._bn_bwd(dy, None, None, R["z3"], R["sc3"], R["sv3"], 0, B, Po, blk.cout,
+                           G[blk.proj[1].weight], G[blk.proj[1].bias], dev)
+        self._wgrad(dz3, R["z2"], G[blk.proj[0].weight], None, B * Po, blk.cout, blk.cexp, in_sc=R["sc2"],
+                    in_act=blk.act, gate=gate, rows_per_sample=Po)
+        dp = torch.empty_like(R["z2"])
+        self._gemm(dz3, blk.proj[0].weight, dp, B * Po, blk.cexp, blk.cout, w_trans=True)
+        dpool = None
+        if blk.se is not None:
+            Sq = blk.se.fc1.out_features
+            dgate = torch.zeros(B, blk.cexp, device=dev, dtype=torch.float32)
+            L.se_bwd_reduce(dp.data_ptr(), R["z2"].data_ptr(), R["sc2"][0].data_ptr(), R["sc2"][1].data_ptr(),
+                            blk.act, dgate.data_ptr(), dc, B, Po, blk.cexp, st)
+            du2 = torch.empty(B, blk.cexp, device=dev, dtype=torch.float32)
+            du1 = torch.empty(B, Sq, device=dev, dtype=torch.float32)
+            dpool = torch.empty(B, blk.cexp, device=dev, dtype=torch.float32)
+            L.se_fc_bwd(dgate.data_ptr(), gate.data_ptr(), R["hidden"].data_ptr(), blk.se.fc1.weight.data_ptr(),
+                        blk.se.fc2.weight.data_ptr(), 1.0 / Po, du2.data_ptr(), du1.data_ptr(), dpool.data_ptr(),
+                        B, blk.cexp, Sq, st)
+            self._wgrad(du2, R["hidden"], G[blk.se.fc2.weight], G[blk.se.fc2.bias], B, blk.cexp, Sq, g_code=0, a_code=0)
+            self._wgrad(du1, R["mean"], G[blk.se.fc1.weight], G[blk.se.fc1.bias], B, Sq, blk.cexp, g_code=0, a_code=0)
+        # depthwise: BN2 + activation (+ SE gate / squeeze gradient composed on the fly)
+        dz2 = self._bn_bwd(dp, gate, dpool, R["z2"], R["sc2"], R["sv2"], blk.act, B, Po, blk.cexp,
+                           G[blk.dw[1].weight], G[blk.dw[1].bias], dev)
+        has_exp = blk.expand is not None
+        dw_in = R["z1"] if has_exp else R["inp"]
+        sc1 = R["sc1"] if has_exp else None
+        L.dw_conv_wgrad(dz2.data_ptr(), dw_in.data_ptr(), _ptr(sc1[0]) if has_exp else 0,
+                        _ptr(sc1[1]) if has_exp else 0, blk.act if has_exp else 0, G[blk.dw[0].weight].data_ptr(),
+                        0, dc, B, Fi, Ti, blk.cexp, blk.k, blk.stride, st)
+        da1 = torch.empty_like(dw_in)
+        # without an expand stage the depthwise input IS the block input: fold the residual gradient in
+        L.dw_conv_dgrad(dz2.data_ptr(), R["wt"].data_ptr(), 0, _ptr(dy) if (blk.res and not has_exp) else 0,
+                        da1.data_ptr(), dc, B, Fi, Ti, blk.cexp, blk.k, blk.stride, st)
+        if has_exp:
+            dz1 = self._bn_bwd(da1, None, None, R["z1"], R["sc1"], R["sv1"], blk.act, B, Pi, blk.cexp,
+                               G[blk.expand[1].weight], G[blk.expand[1].bias], dev)
+            self._wgrad(dz1, R["inp"], G[blk.expand[0].weight], None, B * Pi, blk.cexp, blk.cin)
+            dinp = torch.empty_like(R["inp"])
+            self._gemm(dz1, blk.expand[0].weight, dinp, B * Pi, blk.cin, blk.cexp, w_trans=True,
+                       res=dy if blk.res else None)
+            dy = dinp
+        else:
+            dy = da1
+        return dy
 
     def _backward(self, S, dlogits):
         """-> dict {parameter: fp32 gradient view into one flat arena} (arena returned under key None)."""
@@ -427,55 +503,9 @@ class MNEngine:
         dy = torch.empty_like(Ls["inp"])
         self._gemm(dz, conv.weight, dy, B * P, conv.in_channels, cl, w_trans=True)
 
-        # ---- inverted residual blocks, last to first
+        # ---- blocks, last to first
         for blk, R in zip(reversed(self.blocks), reversed(S["blocks"])):
-            Fi, Ti, Fo, To = R["Fi"], R["Ti"], R["Fo"], R["To"]
-            Pi, Po = Fi * Ti, Fo * To
-            gate = R.get("gate")
-            # project: BN3 (no activation)
-            dz3 = self._bn_bwd(dy, None, None, R["z3"], R["sc3"], R["sv3"], 0, B, Po, blk.cout,
-                               G[blk.proj[1].weight], G[blk.proj[1].bias], dev)
-            self._wgrad(dz3, R["z2"], G[blk.proj[0].weight], None, B * Po, blk.cout, blk.cexp, in_sc=R["sc2"],
-                        in_act=blk.act, gate=gate, rows_per_sample=Po)
-            dp = torch.empty_like(R["z2"])
-            self._gemm(dz3, blk.proj[0].weight, dp, B * Po, blk.cexp, blk.cout, w_trans=True)
-            dpool = None
-            if blk.se is not None:
-                Sq = blk.se.fc1.out_features
-                dgate = torch.zeros(B, blk.cexp, device=dev, dtype=torch.float32)
-                L.se_bwd_reduce(dp.data_ptr(), R["z2"].data_ptr(), R["sc2"][0].data_ptr(), R["sc2"][1].data_ptr(),
-                                blk.act, dgate.data_ptr(), dc, B, Po, blk.cexp, st)
-                du2 = torch.empty(B, blk.cexp, device=dev, dtype=torch.float32)
-                du1 = torch.empty(B, Sq, device=dev, dtype=torch.float32)
-                dpool = torch.empty(B, blk.cexp, device=dev, dtype=torch.float32)
-                L.se_fc_bwd(dgate.data_ptr(), gate.data_ptr(), R["hidden"].data_ptr(), blk.se.fc1.weight.data_ptr(),
-                            blk.se.fc2.weight.data_ptr(), 1.0 / Po, du2.data_ptr(), du1.data_ptr(), dpool.data_ptr(),
-                            B, blk.cexp, Sq, st)
-                self._wgrad(du2, R["hidden"], G[blk.se.fc2.weight], G[blk.se.fc2.bias], B, blk.cexp, Sq, g_code=0, a_code=0)
-                self._wgrad(du1, R["mean"], G[blk.se.fc1.weight], G[blk.se.fc1.bias], B, Sq, blk.cexp, g_code=0, a_code=0)
-            # depthwise: BN2 + activation (+ SE gate / squeeze gradient composed on the fly)
-            dz2 = self._bn_bwd(dp, gate, dpool, R["z2"], R["sc2"], R["sv2"], blk.act, B, Po, blk.cexp,
-                               G[blk.dw[1].weight], G[blk.dw[1].bias], dev)
-            has_exp = blk.expand is not None
-            dw_in = R["z1"] if has_exp else R["inp"]
-            sc1 = R["sc1"] if has_exp else None
-            L.dw_conv_wgrad(dz2.data_ptr(), dw_in.data_ptr(), _ptr(sc1[0]) if has_exp else 0,
-                            _ptr(sc1[1]) if has_exp else 0, blk.act if has_exp else 0, G[blk.dw[0].weight].data_ptr(),
-                            dc, B, Fi, Ti, blk.cexp, blk.k, blk.stride, st)
-            da1 = torch.empty_like(dw_in)
-            # without an expand stage the depthwise input IS the block input: fold the residual gradient in
-            L.dw_conv_dgrad(dz2.data_ptr(), R["wt"].data_ptr(), _ptr(dy) if (blk.res and not has_exp) else 0,
-                            da1.data_ptr(), dc, B, Fi, Ti, blk.cexp, blk.k, blk.stride, st)
-            if has_exp:
-                dz1 = self._bn_bwd(da1, None, None, R["z1"], R["sc1"], R["sv1"], blk.act, B, Pi, blk.cexp,
-                                   G[blk.expand[1].weight], G[blk.expand[1].bias], dev)
-                self._wgrad(dz1, R["inp"], G[blk.expand[0].weight], None, B * Pi, blk.cexp, blk.cin)
-                dinp = torch.empty_like(R["inp"])
-                self._gemm(dz1, blk.expand[0].weight, dinp, B * Pi, blk.cin, blk.cexp, w_trans=True,
-                           res=dy if blk.res else None)
-                dy = dinp
-            else:
-                dy = da1
+            dy = self._block_bwd(blk, R, dy, G, B)
         # ---- stem
         St = S["stem"]
         conv, bn = self.stem[0], self.stem[1]

@@ -147,12 +147,38 @@ int eat_dw_conv_fwd_dy(const void* in, const float* wt, long long wt_bstride, vo
 int eat_ctx_pool(const void* x, int dtype, float* out, int B, int F, int T, int C, cudaStream_t stream);
 /* Sequence pooling of ContextGen (dy_block.py:227-233,249): AvgPool(3, stride, pad 1) or copy (stride 1) of rows
  * [row0, row0+L) of each sample of in [B, Ltot, H] -> out [B, Lo, H]. */
-int eat_seq_pool(const float* in, float* out, int B, int Ltot, int row0, int L, int H, int stride, cudaStream_t stream);
+int eat_seq_pool(const float* in, float* out, int B, int Ltot, int row0, int L, int H, int stride, const float* scale,
+                 const float* shift, int act, cudaStream_t stream);   /* optional affine+act applied to `in` on load */
 /* att [B,k] = softmax((Wr h_c + br)/temperature)  (dy_block.py:104-107). */
 int eat_dyconv_att(const float* hc, const float* wr, const float* br, float temperature, float* att, int B, int H, int k,
                    cudaStream_t stream);
 /* per-sample depthwise weight tables wt [B][ksize^2][C] = sum_j att[b,j] * W[j] (dy_block.py:111-117). */
 int eat_dyconv_mix_dw(const float* w, const float* att, float* wt, int B, int C, int ksize, int k, cudaStream_t stream);
+
+/* DyMN training path.  p = DyReLU-B(BN(z)) * ca_f * ca_t materialised for the projection conv, and its backward:
+ * du = d/d(BN output), dcaf [B,Fo,C] / dcoef [B,C,4] accumulated (caller zeroes), dcat [B,To,C] overwritten. */
+int eat_dy_act_fwd(const void* z, void* out, int dtype, const float* scale, const float* shift, const float* theta,
+                   const float* lam, const float* init, const float* ca_f, const float* ca_t, int B, int Fo, int To,
+                   int C, cudaStream_t stream);
+int eat_dy_act_bwd(const void* dp, const void* z, void* du, int dtype, const float* scale, const float* shift,
+                   const float* theta, const float* lam, const float* init, const float* ca_f, const float* ca_t,
+                   float* dcaf, float* dcat, float* dcoef, int B, int Fo, int To, int C, cudaStream_t stream);
+/* dpre = dcoef * lam * 2 s (1-s) with s = theta (DyReLU coefficient net); out = g * s * (1-s) (sigmoid backward). */
+int eat_dyrelu_coef_bwd(const float* dcoef, const float* theta, const float* lam, float* dpre, long long n,
+                        cudaStream_t stream);
+int eat_sigmoid_bwd(const float* g, const float* s, float* out, long long n, cudaStream_t stream);
+/* softmax(Linear(h_c)/T) backward: dWr/dbr accumulated, dh_c[b,:] += dlogit . Wr. */
+int eat_dyconv_att_bwd(const float* datt, const float* att, float temperature, const float* hc, const float* wr,
+                       float* dwr, float* dbr, float* dhc, int B, int H, int k, cudaStream_t stream);
+int eat_seq_pool_bwd(const float* dout, float* dsrc, int B, int Ltot, int row0, int L, int H, int stride,
+                     cudaStream_t stream);
+int eat_ctx_pool_bwd(const float* dg, void* dx, int dtype, int B, int F, int T, int C, cudaStream_t stream);
+/* Per-sample weight gradients S [B,N,K] of a 1x1 conv on tensor cores, and the DynamicConv bank / attention
+ * gradients derived from per-sample gradients S [B,n]: dW[k] += sum_b att[b,k] S[b]; datt[b,k] = <S[b], W[k]>. */
+int eat_pw_tc_wgrad_persample(const void* G, const void* A, int dtype, float* S, long long M, int N, int K,
+                              int rows_per_sample, cudaStream_t stream);
+int eat_dyn_wgrad_mix(const float* S, const float* att, const float* W, float* dW, float* datt, int B, long long n, int k,
+                      cudaStream_t stream);
 
 /* ---- backward (training step: ex_audioset.py:197 loss.backward() over the modules above) ---- */
 
@@ -191,12 +217,13 @@ int eat_se_fc_bwd(const float* dgate, const float* gate, const float* hidden, co
 
 /* Depthwise conv backward: data gradient (+ optional residual add into din) and weight gradient
  * (dw [C,1,k,k] fp32, atomically accumulated; in may carry the producing layer's BN+act as in_*). */
-int eat_dw_conv_dgrad(const void* dz, const float* wt, const void* res, void* din, int dtype, int B, int F, int T,
-                      int C, int k, int stride, cudaStream_t stream);
-int eat_dw_conv_dgrad_s1(const void* dz, const float* wt, const void* res, void* din, int dtype, int B, int F, int T,
-                         int C, int k, cudaStream_t stream);   /* stride-1 fast path used by eat_dw_conv_dgrad */
+int eat_dw_conv_dgrad(const void* dz, const float* wt, long long wt_bstride, const void* res, void* din, int dtype, int B,
+                      int F, int T, int C, int k, int stride, cudaStream_t stream);
+int eat_dw_conv_dgrad_s1(const void* dz, const float* wt, long long wt_bstride, const void* res, void* din, int dtype,
+                         int B, int F, int T, int C, int k, cudaStream_t stream);   /* stride-1 fast path */
 int eat_dw_conv_wgrad(const void* dz, const void* in, const float* in_scale, const float* in_shift, int in_act,
-                      float* dw, int dtype, int B, int F, int T, int C, int k, int stride, cudaStream_t stream);
+                      float* dw, long long dw_bstride, int dtype, int B, int F, int T, int C, int k, int stride,
+                      cudaStream_t stream);   /* wt_bstride / dw_bstride: floats between per-sample tables (0: shared) */
 /* Stem weight gradient (the spectrogram itself needs no gradient). */
 int eat_stem_wgrad(const void* dz, int dtype, const float* x, float* dw, int B, int F, int T, int C, int stride,
                    cudaStream_t stream);

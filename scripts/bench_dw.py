@@ -31,8 +31,8 @@ for (F, T, C, k, s) in LAYERS:
     stats = torch.zeros(2, C, device="cuda", dtype=torch.float64)
     dz = torch.randn(B, Fo, To, C, device="cuda").to(td); din = torch.empty_like(x); dw = torch.zeros_like(w)
     f_fwd = lambda: L.dw_conv_fwd(x.data_ptr(), wt.data_ptr(), out.data_ptr(), code, B, F, T, C, k, s, sc[0].data_ptr(), sc[1].data_ptr(), 2, 0, 0, 0, 0, stats[0].data_ptr(), stats[1].data_ptr(), st)
-    f_dg = lambda: L.dw_conv_dgrad(dz.data_ptr(), wt.data_ptr(), 0, din.data_ptr(), code, B, F, T, C, k, s, st)
-    f_wg = lambda: L.dw_conv_wgrad(dz.data_ptr(), x.data_ptr(), sc[0].data_ptr(), sc[1].data_ptr(), 2, dw.data_ptr(), code, B, F, T, C, k, s, st)
+    f_dg = lambda: L.dw_conv_dgrad(dz.data_ptr(), wt.data_ptr(), 0, 0, din.data_ptr(), code, B, F, T, C, k, s, st)
+    f_wg = lambda: L.dw_conv_wgrad(dz.data_ptr(), x.data_ptr(), sc[0].data_ptr(), sc[1].data_ptr(), 2, dw.data_ptr(), 0, code, B, F, T, C, k, s, st)
     nb = B * C * es * (F * T + Fo * To)
     t = [timeit(f) for f in (f_fwd, f_dg, f_wg)]
     for i in range(3): tot[i] += t[i]
