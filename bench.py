@@ -35,7 +35,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="clips per GPU per step")
     ap.add_argument("--precision", default=os.environ.get("EAT_PRECISION", "fp32"), choices=["fp32", "bf16"])
-    ap.add_argument("--model", default="mn10")
+    ap.add_argument("--model", default="mn10", choices=["mn04", "mn10", "mn20", "mn40", "dymn04", "dymn10", "dymn20"])
+    ap.add_argument("--mode", default="train", choices=["train", "eval"],
+                    help="train: the headline training step; eval: mel + forward only (BASELINE.json configs[1])")
     ap.add_argument("--cpu-baseline-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -243,12 +245,24 @@ def run_ours(args):
     L.device_check(local)
 
     B = args.batch
-    width = {"mn10": 1.0, "mn04": 0.4, "mn20": 2.0, "mn40": 4.0}[args.model]
+    width = {"mn10": 1.0, "mn04": 0.4, "mn20": 2.0, "mn40": 4.0, "dymn04": 0.4, "dymn10": 1.0, "dymn20": 2.0}[args.model]
+    if args.model.startswith("dymn"):
+        from efficientat_b200.models.dymn.model import get_model
     torch.manual_seed(0)
     with contextlib.redirect_stdout(io.StringIO()):
         model = synth_state_(get_model(width_mult=width, precision=args.precision, verbose=False), seed=7).to(dev)
         mel = AugmentMelSTFT(freqm=0, timem=0).to(dev)          # ex_audioset.py defaults: freqm = timem = 0
     trainer = AudioSetTrainer(model, mel, lr=8e-4, kd_lambda=0.1, mixup_alpha=0.3)
+    if args.mode == "eval":
+        model.eval()
+        mel.eval()
+
+        class _Eval:                                             # same .step() shape as the trainer
+            def step(self, w, y_, t_):
+                with torch.no_grad():
+                    logits, _ = model(mel(w).unsqueeze(1))
+                return logits[:, :2].double().sum(0)             # tiny device result read back in the e2e loop
+        trainer = _Eval()
     import numpy as np
     np.random.seed(rank)
     torch.manual_seed(100 + rank)
@@ -327,11 +341,13 @@ def run_ours(args):
         shares = {k: round(v[0] / sum(x[0] for x in prof.values()), 4) for k, v in
                   sorted(prof.items(), key=lambda kv: -kv[1][0])[:8]}
         line = {
-            "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if (args.mode == "train" and args.model == "mn10") else
+            f"clips/sec (10s@32kHz) {args.model}_as {'fwd+bwd' if args.mode == 'train' else 'fwd'}", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
-            "config": {"workload": f"{args.model}_as training step: mel + mixup + fwd + BCE/KD loss + bwd + Adam "
-                                   f"(ex_audioset.py:135-199), batch {B}/GPU, 10 s @ 32 kHz clips",
+            "config": {"workload": (f"{args.model}_as training step: mel + mixup + fwd + BCE/KD loss + bwd + Adam "
+                                    f"(ex_audioset.py:135-199), batch {B}/GPU, 10 s @ 32 kHz clips") if args.mode == "train"
+                       else f"{args.model}_as mel + eval forward (inference.py:51-53), batch {B}/GPU, 10 s @ 32 kHz clips",
                        "model": f"{args.model}_as", "global_batch": B * world, "parallelism": f"dp{world}",
                        "precision_mode": args.precision,
                        "l2": "inputs (waveforms %.0f MB/GPU) exceed L2; no explicit flush" % (wave.numel() * 4 / 1e6)},

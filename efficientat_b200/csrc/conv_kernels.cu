@@ -7,6 +7,7 @@
 // models/mn/model.py:125-133 and models/mn/block_types.py:140-170; SqueezeExcitation
 // models/mn/block_types.py:72-83.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -128,14 +129,13 @@ struct DyEpi {
   long long wt_bstride;  // floats between the weight tables of consecutive samples (0: shared weights)
 };
 
-template <typename T, int K, int S>
-__global__ void __launch_bounds__(kThreads, 2) dw_kernel(
+template <typename T, int K, int S, int P, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) dw_kernel(
     const T* __restrict__ in, const float* __restrict__ wt, T* __restrict__ out,
     int F, int Tn, int Fo, int To, int C, InXform xf,
     const float* __restrict__ scale, const float* __restrict__ shift, int act, const T* __restrict__ res, int flip,
     float* __restrict__ pool /*[B,C] or null*/, double* __restrict__ stat_sum, double* __restrict__ stat_sq, DyEpi dy) {
   constexpr int V = Vec<T>::N;
-  constexpr int P = (S == 1 && V == 4) ? 8 : 4;
   constexpr int NIN = (P - 1) * S + K;
   constexpr int PAD = (K - 1) / 2;
   extern __shared__ float smem[];
@@ -635,15 +635,23 @@ int launch_dw(const T* in, const float* wt, T* out, int B, int F, int Tn, int C,
     if (!tiled) {
       const int cv = C / V;
       const int ppb = kThreads / cv > 0 ? kThreads / cv : 1;
-      const int units = Fo * ceil_div(To, (stride == 1 && V == 4) ? 8 : 4);
+      static int variant = -1;
+      if (variant < 0) { const char* e = getenv("EAT_DW_VARIANT"); variant = e ? atoi(e) : 3; }   // 3 = 4-wide strips, 4 CTAs/SM: best of the measured variants (profiles/README.md)
+      const int P = (variant == 1 || variant == 3) ? 4 : ((stride == 1 && V == 4) ? 8 : 4);
+      const int units = Fo * ceil_div(To, P);
       int gx = ceil_div(units, ppb);
-      const int cap = max(1, (148 * 8) / max(B, 1));
+      const int cap = max(1, (148 * 16) / max(B, 1));
       if (gx > cap) gx = cap;
       dim3 grid(gx, B);
       size_t smem = 2 * (size_t)C * sizeof(float);
-      if (stride == 1) dw_kernel<T, 3, 1><<<grid, kThreads, smem, st>>>(in, wt, out, F, Tn, Fo, To, C, xf, scale, shift, act, res, flip, pool, ssum, ssq, dy);
-      else if (stride == 2) dw_kernel<T, 3, 2><<<grid, kThreads, smem, st>>>(in, wt, out, F, Tn, Fo, To, C, xf, scale, shift, act, res, flip, pool, ssum, ssq, dy);
-      else { eat_set_error("dw conv: stride must be 1 or 2"); return EAT_ERR_UNSUPPORTED; }
+#define EAT_DWS(SS, PP, MB) dw_kernel<T, 3, SS, PP, MB><<<grid, kThreads, smem, st>>>(in, wt, out, F, Tn, Fo, To, C, xf, scale, shift, act, res, flip, pool, ssum, ssq, dy)
+      if (stride == 1) {
+        if (P == 8) { if (variant == 2) EAT_DWS(1, 8, 3); else EAT_DWS(1, 8, 2); }
+        else { if (variant == 3) EAT_DWS(1, 4, 4); else EAT_DWS(1, 4, 3); }
+      } else if (stride == 2) {
+        if (variant == 3) EAT_DWS(2, 4, 4); else if (variant == 2) EAT_DWS(2, 4, 3); else EAT_DWS(2, 4, 2);
+      } else { eat_set_error("dw conv: stride must be 1 or 2"); return EAT_ERR_UNSUPPORTED; }
+#undef EAT_DWS
       EAT_CHECK_LAUNCH();
       return EAT_OK;
     }

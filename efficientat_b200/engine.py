@@ -49,6 +49,7 @@ class MNEngine:
             raise ValueError(f"precision must be 'fp32' or 'bf16', got {self.precision}")
         self.gemm_impl = os.environ.get("EAT_GEMM", "auto")     # auto | simt (exact-fp32 CUDA cores everywhere)
         self.tc_min_rows = 1024                                  # tiny GEMMs (classifier, SE) stay on CUDA cores
+        self._se_scale = {}
         self._plan()
 
     # ------------------------------------------------------------------ structure
@@ -136,6 +137,22 @@ class MNEngine:
                           sc[0].data_ptr(), sc[1].data_ptr(), sv[0].data_ptr(), sv[1].data_ptr(), c, _stream())
         return sc, sv
 
+    def _se_gate(self, se, pool, inv_count, B, C, dev, hidden=None):
+        """Squeeze-excitation MLP (block_types.py:72-83) as two batched GEMMs: gate = sigmoid(W2 relu(W1 mean + b1) + b2)
+        with mean = pool * inv_count folded into the first epilogue (scale = inv_count, shift = b1)."""
+        S = se.fc1.out_features
+        key = (S, float(inv_count), str(dev))
+        sc = self._se_scale.get(key)
+        if sc is None:
+            sc = torch.full((S,), float(inv_count), device=dev, dtype=torch.float32)
+            self._se_scale[key] = sc
+        if hidden is None:
+            hidden = torch.empty(B, S, device=dev, dtype=torch.float32)
+        self._gemm(pool, se.fc1.weight, hidden, B, S, C, sc=(sc, se.fc1.bias), act=ACT["relu"], a_code=0, c_code=0)
+        gate = torch.empty(B, C, device=dev, dtype=torch.float32)
+        self._gemm(hidden, se.fc2.weight, gate, B, C, S, bias=se.fc2.bias, act=3, a_code=0, c_code=0)
+        return gate, hidden
+
     def _dw_weights(self, conv, dev):
         c, k = conv.out_channels, conv.kernel_size[0]
         wt = torch.empty(k * k, c, device=dev, dtype=torch.float32)
@@ -217,11 +234,7 @@ class MNEngine:
                       _ptr(pool), 0, 0, st)
         gate = None
         if blk.se is not None:
-            gate = torch.empty(B, blk.cexp, device=dev, dtype=torch.float32)
-            S = blk.se.fc1.out_features
-            L.se_fc_fwd(pool.data_ptr(), 1.0 / (Fo * To), blk.se.fc1.weight.data_ptr(),
-                        blk.se.fc1.bias.data_ptr(), blk.se.fc2.weight.data_ptr(), blk.se.fc2.bias.data_ptr(),
-                        gate.data_ptr(), 0, B, blk.cexp, S, st)
+            gate, _ = self._se_gate(blk.se, pool, 1.0 / (Fo * To), B, blk.cexp, dev)
         Mo = B * Fo * To
         o = torch.empty(B, Fo, To, blk.cout, device=dev, dtype=td)
         self._gemm(d, blk.proj[0].weight, o, Mo, blk.cout, blk.cexp, gate=gate, rows_per_sample=Fo * To,
@@ -317,11 +330,7 @@ class MNEngine:
             pool = torch.zeros(B, blk.cexp, device=dev, dtype=torch.float32)
             L.bn_act_pool(z2.data_ptr(), sc2[0].data_ptr(), sc2[1].data_ptr(), blk.act, pool.data_ptr(),
                           1.0 / (Fo * To), dc, B, Fo * To, blk.cexp, st)
-            gate = torch.empty(B, blk.cexp, device=dev, dtype=torch.float32)
-            hidden = torch.empty(B, Sq, device=dev, dtype=torch.float32)
-            L.se_fc_fwd(pool.data_ptr(), 1.0, blk.se.fc1.weight.data_ptr(), blk.se.fc1.bias.data_ptr(),
-                        blk.se.fc2.weight.data_ptr(), blk.se.fc2.bias.data_ptr(), gate.data_ptr(),
-                        hidden.data_ptr(), B, blk.cexp, Sq, st)
+            gate, hidden = self._se_gate(blk.se, pool, 1.0, B, blk.cexp, dev)
             R.update(mean=pool, gate=gate, hidden=hidden)
         z3 = torch.empty(B, Fo, To, blk.cout, device=dev, dtype=td)
         stt = self._new_stats(blk.cout, dev)

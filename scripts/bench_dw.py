@@ -10,6 +10,8 @@ LAYERS = [(64, 500, 16, 3, 1), (64, 500, 64, 3, 2), (32, 250, 72, 3, 1), (32, 25
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--dtype", default="fp32")
+ap.add_argument("--only", type=int, default=-1)
+ap.add_argument("--eval", action="store_true")
 a = ap.parse_args()
 L = lib(); st = torch.cuda.current_stream().cuda_stream
 td = torch.float32 if a.dtype == "fp32" else torch.bfloat16
@@ -22,7 +24,8 @@ def timeit(fn, n=5):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     return sorted(ts)[len(ts) // 2]
 tot = [0.0, 0.0, 0.0]
-for (F, T, C, k, s) in LAYERS:
+for li, (F, T, C, k, s) in enumerate(LAYERS):
+    if a.only >= 0 and li != a.only: continue
     B = a.batch; pad = (k - 1) // 2
     Fo, To = (F + 2 * pad - k) // s + 1, (T + 2 * pad - k) // s + 1
     x = torch.randn(B, F, T, C, device="cuda").to(td); w = torch.randn(C, 1, k, k, device="cuda") * 0.2
@@ -30,7 +33,8 @@ for (F, T, C, k, s) in LAYERS:
     out = torch.empty(B, Fo, To, C, device="cuda", dtype=td); sc = torch.rand(2, C, device="cuda")
     stats = torch.zeros(2, C, device="cuda", dtype=torch.float64)
     dz = torch.randn(B, Fo, To, C, device="cuda").to(td); din = torch.empty_like(x); dw = torch.zeros_like(w)
-    f_fwd = lambda: L.dw_conv_fwd(x.data_ptr(), wt.data_ptr(), out.data_ptr(), code, B, F, T, C, k, s, sc[0].data_ptr(), sc[1].data_ptr(), 2, 0, 0, 0, 0, stats[0].data_ptr(), stats[1].data_ptr(), st)
+    pool = torch.zeros(B, C, device='cuda')
+    f_fwd = (lambda: L.dw_conv_fwd(x.data_ptr(), wt.data_ptr(), out.data_ptr(), code, B, F, T, C, k, s, 0, 0, 0, sc[0].data_ptr(), sc[1].data_ptr(), 2, pool.data_ptr(), 0, 0, st)) if a.eval else (lambda: L.dw_conv_fwd(x.data_ptr(), wt.data_ptr(), out.data_ptr(), code, B, F, T, C, k, s, sc[0].data_ptr(), sc[1].data_ptr(), 2, 0, 0, 0, 0, stats[0].data_ptr(), stats[1].data_ptr(), st))
     f_dg = lambda: L.dw_conv_dgrad(dz.data_ptr(), wt.data_ptr(), 0, 0, din.data_ptr(), code, B, F, T, C, k, s, st)
     f_wg = lambda: L.dw_conv_wgrad(dz.data_ptr(), x.data_ptr(), sc[0].data_ptr(), sc[1].data_ptr(), 2, dw.data_ptr(), 0, code, B, F, T, C, k, s, st)
     nb = B * C * es * (F * T + Fo * To)
