@@ -33,7 +33,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=128, help="clips per GPU per step")
+    ap.add_argument("--batch", type=int, default=256, help="clips per GPU per step")
     ap.add_argument("--precision", default=os.environ.get("EAT_PRECISION", "fp32"), choices=["fp32", "bf16"])
     ap.add_argument("--model", default="mn10", choices=["mn04", "mn10", "mn20", "mn40", "dymn04", "dymn10", "dymn20"])
     ap.add_argument("--mode", default="train", choices=["train", "eval"],

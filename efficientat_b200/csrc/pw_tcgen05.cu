@@ -114,7 +114,7 @@ __device__ __forceinline__ float act_sel(float v, int act) {     // branch-free 
 }
 
 // T: activation storage type.  NP = 1: operands rounded to bf16 (bf16 mode); NP = 2: hi/lo split (fp32 mode).
-template <typename T, int NP, int STAGES, int BN_MAX, bool DYN>
+template <typename T, int NP, int STAGES, int BN_MAX, bool DYN, bool AFF>
 __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {  // 17 warps are allocated as 20: 96 registers/thread is the ceiling
   constexpr int B_TILE_BYTES = BN_MAX * 128;
   constexpr int STAGE_BYTES = NP * (A_TILE_BYTES + B_TILE_BYTES);
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {  // 17
         const float4 sc4 = *reinterpret_cast<const float4*>(s_scale + (cl < BN_MAX ? cl : 0));
         const float4 sh4 = *reinterpret_cast<const float4*>(s_shift + (cl < BN_MAX ? cl : 0));
         float res[8][4];
-        if (R != nullptr) {
+        if (AFF && R != nullptr) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const long long m = mrow0 + i * 4 + rg;
@@ -381,13 +381,15 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {  // 17
 #pragma unroll
             for (int j = 0; j < 4; ++j) { cs[j] += v[j]; cq[j] = fmaf(v[j], v[j], cq[j]); }
             if (nok) {
-              v[0] = act_sel(fmaf(v[0], sc4.x, sh4.x), p.act);
-              v[1] = act_sel(fmaf(v[1], sc4.y, sh4.y), p.act);
-              v[2] = act_sel(fmaf(v[2], sc4.z, sh4.z), p.act);
-              v[3] = act_sel(fmaf(v[3], sc4.w, sh4.w), p.act);
-              if (R != nullptr) {
+              if (AFF) {      // folded BatchNorm / bias + activation (+ residual); compiled out for raw outputs
+                v[0] = act_sel(fmaf(v[0], sc4.x, sh4.x), p.act);
+                v[1] = act_sel(fmaf(v[1], sc4.y, sh4.y), p.act);
+                v[2] = act_sel(fmaf(v[2], sc4.z, sh4.z), p.act);
+                v[3] = act_sel(fmaf(v[3], sc4.w, sh4.w), p.act);
+                if (R != nullptr) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] += res[i][j];
+                  for (int j = 0; j < 4; ++j) v[j] += res[i][j];
+                }
               }
               OutVec<T>::store(C + m * N + n, v);
             }
@@ -433,8 +435,8 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {  // 17
   }
 }
 
-template <typename T, int NP, int STAGES, int BN_MAX, bool DYN>
-int launch_tc(const TcParams& p0, cudaStream_t st) {
+template <typename T, int NP, int STAGES, int BN_MAX, bool DYN, bool AFF>
+int launch_tc_aff(const TcParams& p0, cudaStream_t st) {
   TcParams p = p0;
   p.n_tiles = ceil_div(p.N, BN_MAX);
   p.BN = ceil_div(ceil_div(p.N, p.n_tiles), 16) * 16;
@@ -453,7 +455,7 @@ int launch_tc(const TcParams& p0, cudaStream_t st) {
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(pw_tc_kernel<T, NP, STAGES, BN_MAX, DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(pw_tc_kernel<T, NP, STAGES, BN_MAX, DYN, AFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { eat_set_error(cudaGetErrorString(e)); return EAT_ERR_CUDA; }
     attr_done = true;
   }
@@ -462,9 +464,15 @@ int launch_tc(const TcParams& p0, cudaStream_t st) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < sms ? tiles : sms;
-  pw_tc_kernel<T, NP, STAGES, BN_MAX, DYN><<<grid, kThreads, smem, st>>>(p);
+  pw_tc_kernel<T, NP, STAGES, BN_MAX, DYN, AFF><<<grid, kThreads, smem, st>>>(p);
   EAT_CHECK_LAUNCH();
   return EAT_OK;
+}
+
+template <typename T, int NP, int STAGES, int BN_MAX, bool DYN>
+int launch_tc(const TcParams& p, cudaStream_t st) {
+  const bool aff = p.scale != nullptr || p.shift != nullptr || p.act != 0 || p.residual != nullptr;
+  return aff ? launch_tc_aff<T, NP, STAGES, BN_MAX, DYN, true>(p, st) : launch_tc_aff<T, NP, STAGES, BN_MAX, DYN, false>(p, st);
 }
 
 }  // namespace
