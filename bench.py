@@ -178,6 +178,14 @@ def algo_bytes(name, a):
     return None
 
 
+# DRAM traffic of the dominant kernel from one `ncu --set full` capture (profiles/README.md): dram read + write bytes
+# relative to the algorithmic bytes of the captured launch.  Used to scale the per-launch `traffic` figure.
+NCU_TRAFFIC = {
+    "eat_pw_tc_fwd": {"dram_bytes": 65.619712e6 + 202.606080e6, "algorithmic_bytes": 1024000 * (16 + 64) * 4 + 64 * 16 * 4,
+                      "capture": "profiles/r01_ncu_pw_tc_fwd_K16_N64_M1M_fp32_eval.csv"},
+}
+
+
 class KernelTimer:
     """Wraps the ctypes launchers: CUDA events around launches of the selected C-ABI entry points."""
 
@@ -356,7 +364,12 @@ def run_ours(args):
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks.summary(),
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                         "frac": (achieved / peak) if achieved else None,
+                         "traffic": (top_bytes / max(top_n, 1) * NCU_TRAFFIC[top]["dram_bytes"] / NCU_TRAFFIC[top]["algorithmic_bytes"])
+                         if (top in NCU_TRAFFIC and bytes_ok) else None,
+                         "traffic_source": NCU_TRAFFIC[top]["capture"] + " (dram/algorithmic ratio of the captured launch x "
+                         "this run's algorithmic bytes per launch)" if top in NCU_TRAFFIC else None,
+                         "peak_source": peak_src,
                          "launches_timed": top_n, "avg_launch_ms": top_ms / max(top_n, 1),
                          "algorithmic_bytes_per_launch": top_bytes / max(top_n, 1) if bytes_ok else None},
             "kernel_time_shares": shares,

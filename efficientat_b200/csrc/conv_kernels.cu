@@ -129,19 +129,22 @@ struct DyEpi {
   long long wt_bstride;  // floats between the weight tables of consecutive samples (0: shared weights)
 };
 
-template <typename T, int K, int S, int P, int MINB>
+// MODE 0: training forward (optional input BN+act, raw output + batch statistics)
+// MODE 1: eval forward (folded BN + act epilogue, SE pooling, DyMN epilogue)     MODE 2: stride-1 data gradient
+template <typename T, int K, int S, int P, int MINB, int MODE>
 __global__ void __launch_bounds__(kThreads, MINB) dw_kernel(
     const T* __restrict__ in, const float* __restrict__ wt, T* __restrict__ out,
     int F, int Tn, int Fo, int To, int C, InXform xf,
     const float* __restrict__ scale, const float* __restrict__ shift, int act, const T* __restrict__ res, int flip,
     float* __restrict__ pool /*[B,C] or null*/, double* __restrict__ stat_sum, double* __restrict__ stat_sq, DyEpi dy) {
   constexpr int V = Vec<T>::N;
+  constexpr bool kAff = MODE == 1, kStats = MODE == 0, kXf = MODE == 0, kRes = MODE == 2, kDy = MODE == 1, kPool = MODE == 1;
   constexpr int NIN = (P - 1) * S + K;
   constexpr int PAD = (K - 1) / 2;
   extern __shared__ float smem[];
   float* s_sum = smem;       // [C]
   float* s_sq = smem + C;    // [C]
-  const bool need_red = (pool != nullptr) || (stat_sum != nullptr);
+  const bool need_red = (kPool && pool != nullptr) || (kStats && stat_sum != nullptr);
   if (need_red) {
     for (int i = threadIdx.x; i < 2 * C; i += kThreads) s_sum[i] = 0.f;
     __syncthreads();
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(kThreads, MINB) dw_kernel(
   for (int i = 0; i < V; ++i) { lsum[i] = 0.f; lsq[i] = 0.f; }
   const T* inb = in + (size_t)b * F * Tn * C;
   T* outb = out + (size_t)b * Fo * To * C;
-  const T* resb = res != nullptr ? res + (size_t)b * Fo * To * C : nullptr;
+  const T* resb = (kRes && res != nullptr) ? res + (size_t)b * Fo * To * C : nullptr;
   wt += (size_t)b * dy.wt_bstride;
   // channel vectors beyond kThreads are covered by looping cvi
   for (int cvi = threadIdx.x % (cv < kThreads ? cv : kThreads); cvi < cv; cvi += kThreads) {
@@ -164,12 +167,12 @@ __global__ void __launch_bounds__(kThreads, MINB) dw_kernel(
     if (slot >= ppb) break;
     const int c0 = cvi * V;
     float isc[V], ish[V];
-    if (xf.scale != nullptr) {
+    if (kXf && xf.scale != nullptr) {
 #pragma unroll
       for (int i = 0; i < V; ++i) { isc[i] = xf.scale[c0 + i]; ish[i] = xf.shift[c0 + i]; }
     }
     float da1[V], da2[V], db1[V], db2[V];
-    if (dy.theta != nullptr) {
+    if (kDy && dy.theta != nullptr) {
       const float* th = dy.theta + ((size_t)b * C + c0) * 4;
 #pragma unroll
       for (int i = 0; i < V; ++i) {
@@ -210,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, MINB) dw_kernel(
           if (t < 0 || t >= Tn) continue;
           float v[V];
           Vec<T>::load(rowp + (size_t)t * C, v);
-          if (xf.scale != nullptr) {
+          if (kXf && xf.scale != nullptr) {
 #pragma unroll
             for (int i = 0; i < V; ++i) v[i] = act_fwd(fmaf(v[i], isc[i], ish[i]), xf.act);
           }
@@ -229,18 +232,21 @@ __global__ void __launch_bounds__(kThreads, MINB) dw_kernel(
         const int to = to0 + p;
         if (to >= To) break;
         float o[V];
-        if (scale != nullptr) {
+        if (kAff && scale != nullptr) {
 #pragma unroll
           for (int i = 0; i < V; ++i) { o[i] = act_fwd(fmaf(acc[p][i], scale[c0 + i], shift[c0 + i]), act); lsum[i] += o[i]; }
         } else {
 #pragma unroll
-          for (int i = 0; i < V; ++i) { o[i] = acc[p][i]; lsum[i] += o[i]; lsq[i] = fmaf(o[i], o[i], lsq[i]); }
+          for (int i = 0; i < V; ++i) {
+            o[i] = acc[p][i];
+            if (kStats) { lsum[i] += o[i]; lsq[i] = fmaf(o[i], o[i], lsq[i]); }
+          }
         }
-        if (dy.theta != nullptr) {
+        if (kDy && dy.theta != nullptr) {
 #pragma unroll
           for (int i = 0; i < V; ++i) o[i] = fmaxf(fmaf(o[i], da1[i], db1[i]), fmaf(o[i], da2[i], db2[i]));
         }
-        if (dy.ca_f != nullptr) {
+        if (kDy && dy.ca_f != nullptr) {
           const float* cf = dy.ca_f + ((size_t)b * Fo + fo) * C + c0;
           const float* ct = dy.ca_t + ((size_t)b * To + to) * C + c0;
 #pragma unroll
@@ -262,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, MINB) dw_kernel(
     if (need_red) {
 #pragma unroll
       for (int i = 0; i < V; ++i) { atomicAdd(&s_sum[c0 + i], lsum[i]); lsum[i] = 0.f; }
-      if (stat_sum != nullptr) {
+      if (kStats && stat_sum != nullptr) {
 #pragma unroll
         for (int i = 0; i < V; ++i) { atomicAdd(&s_sq[c0 + i], lsq[i]); lsq[i] = 0.f; }
       }
@@ -271,8 +277,8 @@ __global__ void __launch_bounds__(kThreads, MINB) dw_kernel(
   if (need_red) {
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += kThreads) {
-      if (pool != nullptr) atomicAdd(pool + (size_t)b * C + c, s_sum[c]);
-      if (stat_sum != nullptr) { atomicAdd(stat_sum + c, (double)s_sum[c]); atomicAdd(stat_sq + c, (double)s_sq[c]); }
+      if (kPool && pool != nullptr) atomicAdd(pool + (size_t)b * C + c, s_sum[c]);
+      if (kStats && stat_sum != nullptr) { atomicAdd(stat_sum + c, (double)s_sum[c]); atomicAdd(stat_sq + c, (double)s_sq[c]); }
     }
   }
 }
@@ -282,12 +288,13 @@ __global__ void __launch_bounds__(kThreads, MINB) dw_kernel(
 // ((FR-1)*S+K rows x (TT-1)*S+K columns x 32 channels) in shared memory as fp32, applying the producing layer's
 // BatchNorm + activation ONCE per element (the register-strip kernel re-applies it for every kernel row), then
 // every thread computes a strip of P outputs for one 4-channel vector from shared memory (LDS.128).
-template <typename T, int K, int S>
-__global__ void __launch_bounds__(kThreads) dw_tile_kernel(
+template <typename T, int K, int S, int MODE>
+__global__ void __launch_bounds__(kThreads, 3) dw_tile_kernel(
     const T* __restrict__ in, const float* __restrict__ wt, T* __restrict__ out,
     int F, int Tn, int Fo, int To, int C, InXform xf,
     const float* __restrict__ scale, const float* __restrict__ shift, int act, const T* __restrict__ res, int flip,
     float* __restrict__ pool, double* __restrict__ stat_sum, double* __restrict__ stat_sq, DyEpi dy) {
+  constexpr bool kAff = MODE == 1, kStats = MODE == 0, kXf = MODE == 0, kRes = MODE == 2, kDy = MODE == 1, kPool = MODE == 1;
   constexpr int VG = Vec<T>::N;                 // channels per 16-byte global vector
   constexpr int CC = 32;                        // channels per tile
   constexpr int CCV = CC / 4;
@@ -308,10 +315,10 @@ __global__ void __launch_bounds__(kThreads) dw_tile_kernel(
   const int b = blockIdx.y;
   const int tiles_t = ceil_div(To, TT), tiles_f = ceil_div(Fo, FR), chunks = ceil_div(C, CC);
   const int tiles_per_chunk = tiles_t * tiles_f;
-  const bool need_red = (pool != nullptr) || (stat_sum != nullptr);
+  const bool need_red = (kPool && pool != nullptr) || (kStats && stat_sum != nullptr);
   const T* inb = in + (size_t)b * F * Tn * C;
   T* outb = out + (size_t)b * Fo * To * C;
-  const T* resb = res != nullptr ? res + (size_t)b * Fo * To * C : nullptr;
+  const T* resb = (kRes && res != nullptr) ? res + (size_t)b * Fo * To * C : nullptr;
   wt += (size_t)b * dy.wt_bstride;
   const int tid = threadIdx.x;
   // blockIdx.x enumerates (channel chunk, tile group); each CTA walks its tile group with a stride
@@ -333,7 +340,7 @@ __global__ void __launch_bounds__(kThreads) dw_tile_kernel(
   const int lc0 = cbase + lv * VG;              // first channel of that vector
   const bool lvalid = lc0 < C;
   float isc[VG], ish[VG];
-  if (xf.scale != nullptr && lvalid) {
+  if (kXf && xf.scale != nullptr && lvalid) {
 #pragma unroll
     for (int i = 0; i < VG; ++i) { isc[i] = xf.scale[lc0 + i]; ish[i] = xf.shift[lc0 + i]; }
   }
@@ -344,11 +351,11 @@ __global__ void __launch_bounds__(kThreads) dw_tile_kernel(
   float osc[4], osh[4], lsum[4] = {0.f, 0.f, 0.f, 0.f}, lsq[4] = {0.f, 0.f, 0.f, 0.f};
   float da1[4], da2[4], db1[4], db2[4];
   if (cvalid) {
-    if (scale != nullptr) {
+    if (kAff && scale != nullptr) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) { osc[i] = scale[c0 + i]; osh[i] = shift[c0 + i]; }
     }
-    if (dy.theta != nullptr) {
+    if (kDy && dy.theta != nullptr) {
       const float* th = dy.theta + ((size_t)b * C + c0) * 4;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -372,7 +379,7 @@ __global__ void __launch_bounds__(kThreads) dw_tile_kernel(
       float v[VG];
       if (lvalid && f >= 0 && f < F && t >= 0 && t < Tn) {
         Vec<T>::load(inb + ((size_t)f * Tn + t) * C + lc0, v);
-        if (xf.scale != nullptr) {
+        if (kXf && xf.scale != nullptr) {
 #pragma unroll
           for (int i = 0; i < VG; ++i) v[i] = act_fwd(fmaf(v[i], isc[i], ish[i]), xf.act);
         }
@@ -422,18 +429,21 @@ __global__ void __launch_bounds__(kThreads) dw_tile_kernel(
           const int to = to0 + p;
           if (to >= To) break;
           float o[4];
-          if (scale != nullptr) {
+          if (kAff && scale != nullptr) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) { o[i] = act_fwd(fmaf(acc[p][i], osc[i], osh[i]), act); lsum[i] += o[i]; }
           } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { o[i] = acc[p][i]; lsum[i] += o[i]; lsq[i] = fmaf(o[i], o[i], lsq[i]); }
+            for (int i = 0; i < 4; ++i) {
+              o[i] = acc[p][i];
+              if (kStats) { lsum[i] += o[i]; lsq[i] = fmaf(o[i], o[i], lsq[i]); }
+            }
           }
-          if (dy.theta != nullptr) {
+          if (kDy && dy.theta != nullptr) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) o[i] = fmaxf(fmaf(o[i], da1[i], db1[i]), fmaf(o[i], da2[i], db2[i]));
           }
-          if (dy.ca_f != nullptr) {
+          if (kDy && dy.ca_f != nullptr) {
             const float4 f4 = __ldg(reinterpret_cast<const float4*>(dy.ca_f + ((size_t)b * Fo + fo) * C + c0));
             const float4 t4 = __ldg(reinterpret_cast<const float4*>(dy.ca_t + ((size_t)b * To + to) * C + c0));
             o[0] *= f4.x * t4.x; o[1] *= f4.y * t4.y; o[2] *= f4.z * t4.z; o[3] *= f4.w * t4.w;
@@ -455,13 +465,13 @@ __global__ void __launch_bounds__(kThreads) dw_tile_kernel(
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         atomicAdd(&s_sum[cvec * 4 + i], lsum[i]);
-        if (stat_sum != nullptr) atomicAdd(&s_sq[cvec * 4 + i], lsq[i]);
+        if (kStats && stat_sum != nullptr) atomicAdd(&s_sq[cvec * 4 + i], lsq[i]);
       }
     }
     __syncthreads();
     if (tid < CC && cbase + tid < C) {
-      if (pool != nullptr) atomicAdd(pool + (size_t)b * C + cbase + tid, s_sum[tid]);
-      if (stat_sum != nullptr) { atomicAdd(stat_sum + cbase + tid, (double)s_sum[tid]); atomicAdd(stat_sq + cbase + tid, (double)s_sq[tid]); }
+      if (kPool && pool != nullptr) atomicAdd(pool + (size_t)b * C + cbase + tid, s_sum[tid]);
+      if (kStats && stat_sum != nullptr) { atomicAdd(stat_sum + cbase + tid, (double)s_sum[tid]); atomicAdd(stat_sq + cbase + tid, (double)s_sq[tid]); }
     }
   }
 }
@@ -635,22 +645,23 @@ int launch_dw(const T* in, const float* wt, T* out, int B, int F, int Tn, int C,
     if (!tiled) {
       const int cv = C / V;
       const int ppb = kThreads / cv > 0 ? kThreads / cv : 1;
-      static int variant = -1;
-      if (variant < 0) { const char* e = getenv("EAT_DW_VARIANT"); variant = e ? atoi(e) : 3; }   // 3 = 4-wide strips, 4 CTAs/SM: best of the measured variants (profiles/README.md)
-      const int P = (variant == 1 || variant == 3) ? 4 : ((stride == 1 && V == 4) ? 8 : 4);
+      const int P = 4;      // 4-wide strips at 4 CTAs/SM measured best among {4,8} x {2,3,4} (profiles/README.md)
       const int units = Fo * ceil_div(To, P);
       int gx = ceil_div(units, ppb);
       const int cap = max(1, (148 * 16) / max(B, 1));
       if (gx > cap) gx = cap;
       dim3 grid(gx, B);
       size_t smem = 2 * (size_t)C * sizeof(float);
-#define EAT_DWS(SS, PP, MB) dw_kernel<T, 3, SS, PP, MB><<<grid, kThreads, smem, st>>>(in, wt, out, F, Tn, Fo, To, C, xf, scale, shift, act, res, flip, pool, ssum, ssq, dy)
-      if (stride == 1) {
-        if (P == 8) { if (variant == 2) EAT_DWS(1, 8, 3); else EAT_DWS(1, 8, 2); }
-        else { if (variant == 3) EAT_DWS(1, 4, 4); else EAT_DWS(1, 4, 3); }
-      } else if (stride == 2) {
-        if (variant == 3) EAT_DWS(2, 4, 4); else if (variant == 2) EAT_DWS(2, 4, 3); else EAT_DWS(2, 4, 2);
-      } else { eat_set_error("dw conv: stride must be 1 or 2"); return EAT_ERR_UNSUPPORTED; }
+      const int mode = (scale != nullptr || pool != nullptr || dy.theta != nullptr || dy.ca_f != nullptr) ? 1 : ((flip || res != nullptr) ? 2 : 0);
+#define EAT_DWS(SS, PP, MB)                                                                                         \
+  do {                                                                                                              \
+    if (mode == 0) dw_kernel<T, 3, SS, PP, MB, 0><<<grid, kThreads, smem, st>>>(in, wt, out, F, Tn, Fo, To, C, xf, scale, shift, act, res, flip, pool, ssum, ssq, dy); \
+    else if (mode == 1) dw_kernel<T, 3, SS, PP, MB, 1><<<grid, kThreads, smem, st>>>(in, wt, out, F, Tn, Fo, To, C, xf, scale, shift, act, res, flip, pool, ssum, ssq, dy); \
+    else dw_kernel<T, 3, SS, PP, MB, 2><<<grid, kThreads, smem, st>>>(in, wt, out, F, Tn, Fo, To, C, xf, scale, shift, act, res, flip, pool, ssum, ssq, dy); \
+  } while (0)
+      if (stride == 1) EAT_DWS(1, 4, 4);
+      else if (stride == 2) EAT_DWS(2, 4, 4);
+      else { eat_set_error("dw conv: stride must be 1 or 2"); return EAT_ERR_UNSUPPORTED; }
 #undef EAT_DWS
       EAT_CHECK_LAUNCH();
       return EAT_OK;
@@ -665,17 +676,18 @@ int launch_dw(const T* in, const float* wt, T* out, int B, int F, int Tn, int C,
   if (groups > tiles) groups = tiles;
   dim3 grid(chunks * groups, B);
   size_t smem = ((size_t)IR * IT * 32 + (size_t)k * k * 32 + 64) * sizeof(float);
-#define EAT_DW(KK, SS)                                                                                          \
+  const int tmode = (scale != nullptr || pool != nullptr || dy.theta != nullptr || dy.ca_f != nullptr) ? 1 : ((flip || res != nullptr) ? 2 : 0);
+#define EAT_DWM(KK, SS, MM)                                                                                     \
   do {                                                                                                          \
     static bool attr = false;                                                                                   \
-    if (!attr) { cudaFuncSetAttribute(dw_tile_kernel<T, KK, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; } \
-    dw_tile_kernel<T, KK, SS><<<grid, kThreads, smem, st>>>(in, wt, out, F, Tn, Fo, To, C, xf, scale, shift, act, res, flip, pool, ssum, ssq, dy); \
+    if (!attr) { cudaFuncSetAttribute(dw_tile_kernel<T, KK, SS, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; } \
+    dw_tile_kernel<T, KK, SS, MM><<<grid, kThreads, smem, st>>>(in, wt, out, F, Tn, Fo, To, C, xf, scale, shift, act, res, flip, pool, ssum, ssq, dy); \
   } while (0)
-  if (k == 3 && stride == 1) EAT_DW(3, 1);
-  else if (k == 3 && stride == 2) EAT_DW(3, 2);
-  else if (k == 5 && stride == 1) EAT_DW(5, 1);
+#define EAT_DW(KK, SS) do { if (tmode == 0) EAT_DWM(KK, SS, 0); else if (tmode == 1) EAT_DWM(KK, SS, 1); else EAT_DWM(KK, SS, 2); } while (0)
+  if (k == 5 && stride == 1) EAT_DW(5, 1);
   else if (k == 5 && stride == 2) EAT_DW(5, 2);
   else { eat_set_error("dw conv: only k in {3,5}, stride in {1,2}"); return EAT_ERR_UNSUPPORTED; }
+#undef EAT_DWM
 #undef EAT_DW
   EAT_CHECK_LAUNCH();
   return EAT_OK;

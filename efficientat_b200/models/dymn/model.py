@@ -12,6 +12,7 @@ import torch
 from torch import Tensor, nn
 from torch.hub import load_state_dict_from_url
 
+from ..common import check_head, check_setting, mlp_head, reference_init_, v3_large_rows
 from ..mn.block_types import ConvNormActivation, InvertedResidual
 from .dy_block import DY_Block, DynamicConv, DynamicInvertedResidualConfig
 
@@ -27,6 +28,8 @@ pretrained_models = {k: urllib.parse.urljoin(model_url, v) for k, v in _release_
 
 
 class DyMN(nn.Module):
+    """in_c (stem) -> layers[15] (DY_Block | InvertedResidual) -> out_c (1x1) -> classifier; parameter container."""
+
     def __init__(self, inverted_residual_setting: List[DynamicInvertedResidualConfig], last_channel: int,
                  num_classes: int = 527, head_type: str = "mlp", block: Optional[Callable[..., nn.Module]] = None,
                  norm_layer: Optional[Callable[..., nn.Module]] = None, dropout: float = 0.2,
@@ -35,60 +38,27 @@ class DyMN(nn.Module):
                  no_dyrelu: bool = False, no_dyconv: bool = False, no_ca: bool = False,
                  temp_schedule: tuple = (30, 1, 1, 0.05), **kwargs: Any) -> None:
         super().__init__()
-        if not inverted_residual_setting:
-            raise ValueError("The inverted_residual_setting should not be empty")
-        if not (isinstance(inverted_residual_setting, Sequence)
-                and all(isinstance(s, DynamicInvertedResidualConfig) for s in inverted_residual_setting)):
-            raise TypeError("The inverted_residual_setting should be List[DynamicInvertedResidualConfig]")
-        if block is None:
-            block = DY_Block
+        check_setting(inverted_residual_setting, DynamicInvertedResidualConfig)
+        check_head(head_type)
         if in_conv_kernel != 3 or in_channels != 1:
             raise NotImplementedError("the fused stem kernel implements a 3x3 convolution on 1 input channel")
-        if norm_layer is None:
-            norm_layer = partial(nn.BatchNorm2d, eps=0.001, momentum=0.01)
+        make_block = DY_Block if block is None else block
+        bn = partial(nn.BatchNorm2d, eps=0.001, momentum=0.01) if norm_layer is None else norm_layer
+        dy_kwargs = dict(context_ratio=context_ratio, max_context_size=max_context_size,
+                         min_context_size=min_context_size, dyrelu_k=dyrelu_k, dyconv_k=dyconv_k, no_dyrelu=no_dyrelu,
+                         no_dyconv=no_dyconv, no_ca=no_ca, temp_schedule=temp_schedule)
+        first, last = inverted_residual_setting[0], inverted_residual_setting[-1]
         self.layers = nn.ModuleList()
-        self.in_c = ConvNormActivation(in_channels, inverted_residual_setting[0].input_channels,
-                                       kernel_size=in_conv_kernel, stride=in_conv_stride, norm_layer=norm_layer,
-                                       activation_layer=nn.Hardswish)
+        self.in_c = ConvNormActivation(in_channels, first.input_channels, kernel_size=in_conv_kernel,
+                                       stride=in_conv_stride, norm_layer=bn, activation_layer=nn.Hardswish)
         for cnf in inverted_residual_setting:
-            if cnf.use_dy_block:
-                b = block(cnf, context_ratio=context_ratio, max_context_size=max_context_size,
-                          min_context_size=min_context_size, dyrelu_k=dyrelu_k, dyconv_k=dyconv_k,
-                          no_dyrelu=no_dyrelu, no_dyconv=no_dyconv, no_ca=no_ca, temp_schedule=temp_schedule)
-            else:
-                b = InvertedResidual(cnf, None, norm_layer, partial(nn.BatchNorm2d, eps=0.001, momentum=0.01))
-            self.layers.append(b)
-        last_in = inverted_residual_setting[-1].out_channels
-        last_out = 6 * last_in
-        self.out_c = ConvNormActivation(last_in, last_out, kernel_size=1, norm_layer=norm_layer,
+            self.layers.append(make_block(cnf, **dy_kwargs) if cnf.use_dy_block else
+                               InvertedResidual(cnf, None, bn, partial(nn.BatchNorm2d, eps=0.001, momentum=0.01)))
+        self.out_c = ConvNormActivation(last.out_channels, 6 * last.out_channels, kernel_size=1, norm_layer=bn,
                                         activation_layer=nn.Hardswish)
         self.head_type = head_type
-        if head_type == "mlp":
-            self.classifier = nn.Sequential(
-                nn.AdaptiveAvgPool2d(1),
-                nn.Flatten(start_dim=1),
-                nn.Linear(last_out, last_channel),
-                nn.Hardswish(inplace=True),
-                nn.Dropout(p=dropout, inplace=True),
-                nn.Linear(last_channel, num_classes),
-            )
-        elif head_type == "fully_convolutional":
-            raise NotImplementedError("head_type 'fully_convolutional' is not implemented by the fused engine")
-        else:
-            raise NotImplementedError(f"Head '{head_type}' unknown. Must be one of: 'mlp', "
-                                      f"'fully_convolutional', 'multihead_attention_pooling'")
-        for m in self.modules():                                                   # dymn/model.py:141-152
-            if isinstance(m, nn.Conv2d):
-                nn.init.kaiming_normal_(m.weight, mode="fan_out")
-                if m.bias is not None:
-                    nn.init.zeros_(m.bias)
-            elif isinstance(m, (nn.BatchNorm2d, nn.GroupNorm, nn.LayerNorm, nn.InstanceNorm2d)):
-                nn.init.ones_(m.weight)
-                nn.init.zeros_(m.bias)
-            elif isinstance(m, nn.Linear):
-                nn.init.normal_(m.weight, 0, 0.01)
-                if m.bias is not None:
-                    nn.init.zeros_(m.bias)
+        self.classifier = mlp_head(6 * last.out_channels, last_channel, num_classes, dropout)
+        reference_init_(self)
         self._engine = None
         self.precision = kwargs.get("precision", "fp32")
 
@@ -100,51 +70,34 @@ class DyMN(nn.Module):
 
     def _forward_impl(self, x: Tensor, return_fmaps: bool = False):
         logits, embed, fmaps = self.engine().forward(x, return_fmaps=return_fmaps)
-        if return_fmaps:
-            return logits, fmaps
-        return logits, embed
+        return (logits, fmaps) if return_fmaps else (logits, embed)
 
     def forward(self, x: Tensor, return_fmaps: bool = False):
         return self._forward_impl(x, return_fmaps)
 
     def update_params(self, epoch):
+        """per-epoch DynamicConv temperature update (ex_audioset.py:132-133)"""
         for module in self.modules():
             if isinstance(module, DynamicConv):
                 module.update_params(epoch)
 
 
+_REPLACE_SE = (3, 4, 5, 10, 11, 12, 13, 14)       # rows that carry squeeze-excitation in MobileNetV3
+
+
 def _dymn_conf(width_mult: float = 1.0, reduced_tail: bool = False, dilated: bool = False,
                strides: Tuple[int, ...] = (2, 2, 2, 2), use_dy_blocks: str = "all", **kwargs: Any):
-    """dymn/model.py:209-254"""
-    div = 2 if reduced_tail else 1
-    dil = 2 if dilated else 1
+    """15 block configs + classifier width (reference models/dymn/model.py:209-254)."""
+    rows, last = v3_large_rows(strides, reduced_tail, dilated)
     if use_dy_blocks == "all":
-        dy = [True] * 15
+        dynamic = [True] * len(rows)
     elif use_dy_blocks == "replace_se":
-        dy = [False, False, False, True, True, True, False, False, False, False, True, True, True, True, True]
+        dynamic = [i in _REPLACE_SE for i in range(len(rows))]
     else:
         raise NotImplementedError(f"Config use_dy_blocks={use_dy_blocks} not implemented.")
-    rows = [
-        (16, 3, 16, 16, "RE", 1, 1),
-        (16, 3, 64, 24, "RE", strides[0], 1),
-        (24, 3, 72, 24, "RE", 1, 1),
-        (24, 5, 72, 40, "RE", strides[1], 1),
-        (40, 5, 120, 40, "RE", 1, 1),
-        (40, 5, 120, 40, "RE", 1, 1),
-        (40, 3, 240, 80, "HS", strides[2], 1),
-        (80, 3, 200, 80, "HS", 1, 1),
-        (80, 3, 184, 80, "HS", 1, 1),
-        (80, 3, 184, 80, "HS", 1, 1),
-        (80, 3, 480, 112, "HS", 1, 1),
-        (112, 3, 672, 112, "HS", 1, 1),
-        (112, 5, 672, 160 // div, "HS", strides[3], dil),
-        (160 // div, 5, 960 // div, 160 // div, "HS", 1, dil),
-        (160 // div, 5, 960 // div, 160 // div, "HS", 1, dil),
-    ]
-    setting = [DynamicInvertedResidualConfig(cin, k, cexp, cout, dy[i], act, s, d, width_mult)
-               for i, (cin, k, cexp, cout, act, s, d) in enumerate(rows)]
-    last_channel = DynamicInvertedResidualConfig.adjust_channels(1280 // div, width_mult)
-    return setting, last_channel
+    setting = [DynamicInvertedResidualConfig(cin, k, cexp, cout, dynamic[i], act, stride, dil, width_mult)
+               for i, (cin, k, cexp, cout, _se, act, stride, dil) in enumerate(rows)]
+    return setting, DynamicInvertedResidualConfig.adjust_channels(last, width_mult)
 
 
 def _dymn(inverted_residual_setting, last_channel, pretrained_name, **kwargs):

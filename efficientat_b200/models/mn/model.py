@@ -13,7 +13,8 @@ import torch
 from torch import Tensor, nn
 from torch.hub import load_state_dict_from_url
 
-from ..mn.block_types import ConvNormActivation, FusedOnly, InvertedResidual, InvertedResidualConfig
+from ..common import check_head, check_setting, mlp_head, reference_init_, v3_large_rows
+from ..mn.block_types import ConvNormActivation, InvertedResidual, InvertedResidualConfig
 from ..mn.utils import cnn_out_size
 
 # release assets of the reference (models/mn/model.py:18-70); only the names are needed here
@@ -39,74 +40,39 @@ pretrained_models = {k: urllib.parse.urljoin(model_url, v) for k, v in _release_
 
 
 class MN(nn.Module):
+    """features[0] stem -> features[1..15] InvertedResidual -> features[16] 1x1 conv -> classifier; parameter container."""
+
     def __init__(self, inverted_residual_setting: List[InvertedResidualConfig], last_channel: int,
                  num_classes: int = 1000, block: Optional[Callable[..., nn.Module]] = None,
                  norm_layer: Optional[Callable[..., nn.Module]] = None, dropout: float = 0.2,
                  in_conv_kernel: int = 3, in_conv_stride: int = 2, in_channels: int = 1, **kwargs: Any) -> None:
         super().__init__()
-        if not inverted_residual_setting:
-            raise ValueError("The inverted_residual_setting should not be empty")
-        if not (isinstance(inverted_residual_setting, Sequence)
-                and all(isinstance(s, InvertedResidualConfig) for s in inverted_residual_setting)):
-            raise TypeError("The inverted_residual_setting should be List[InvertedResidualConfig]")
-        if block is None:
-            block = InvertedResidual
+        check_setting(inverted_residual_setting, InvertedResidualConfig)
+        self.head_type = kwargs.get("head_type", False)
+        check_head(self.head_type)
         if in_conv_kernel != 3 or in_channels != 1:
             raise NotImplementedError("the fused stem kernel implements a 3x3 convolution on 1 input channel")
-        if norm_layer is None:
-            norm_layer = partial(nn.BatchNorm2d, eps=0.001, momentum=0.01)       # mn/model.py:114-115
-        depthwise_norm_layer = norm_layer
-
-        stem_out = inverted_residual_setting[0].input_channels
-        layers: List[nn.Module] = [ConvNormActivation(in_channels, stem_out, kernel_size=in_conv_kernel,
-                                                      stride=in_conv_stride, norm_layer=norm_layer,
-                                                      activation_layer=nn.Hardswish)]
+        make_block = InvertedResidual if block is None else block
+        bn = partial(nn.BatchNorm2d, eps=0.001, momentum=0.01) if norm_layer is None else norm_layer   # mn/model.py:114-115
         se_cnf = kwargs.get("se_conf", None)
-        f_dim, t_dim = kwargs.get("input_dims", (128, 1000))
-        f_dim = cnn_out_size(f_dim, 1, 1, 3, 2)
-        t_dim = cnn_out_size(t_dim, 1, 1, 3, 2)
+        first, last = inverted_residual_setting[0], inverted_residual_setting[-1]
+        # spatial sizes are tracked only because squeeze-excitation over f / t would need them (mn/model.py:138-151)
+        f_dim, t_dim = (cnn_out_size(d, 1, 1, 3, 2) for d in kwargs.get("input_dims", (128, 1000)))
+        layers: List[nn.Module] = [ConvNormActivation(in_channels, first.input_channels, kernel_size=in_conv_kernel,
+                                                      stride=in_conv_stride, norm_layer=bn,
+                                                      activation_layer=nn.Hardswish)]
         for cnf in inverted_residual_setting:
             f_dim, t_dim = cnf.out_size(f_dim), cnf.out_size(t_dim)
             cnf.f_dim, cnf.t_dim = f_dim, t_dim
-            layers.append(block(cnf, se_cnf, norm_layer, depthwise_norm_layer))
-        last_in = inverted_residual_setting[-1].out_channels
-        last_out = 6 * last_in
-        layers.append(ConvNormActivation(last_in, last_out, kernel_size=1, norm_layer=norm_layer,
+            layers.append(make_block(cnf, se_cnf, bn, bn))
+        layers.append(ConvNormActivation(last.out_channels, 6 * last.out_channels, kernel_size=1, norm_layer=bn,
                                          activation_layer=nn.Hardswish))
         self.features = nn.Sequential(*layers)
-
-        self.head_type = kwargs.get("head_type", False)
-        if self.head_type == "mlp":
-            self.classifier = nn.Sequential(
-                nn.AdaptiveAvgPool2d(1),
-                nn.Flatten(start_dim=1),
-                nn.Linear(last_out, last_channel),
-                nn.Hardswish(inplace=True),
-                nn.Dropout(p=dropout, inplace=True),
-                nn.Linear(last_channel, num_classes),
-            )
-        elif self.head_type in ("fully_convolutional", "multihead_attention_pooling"):
-            raise NotImplementedError(f"head_type '{self.head_type}' is not implemented by the fused engine "
-                                      "(all released *_as checkpoints used by the benchmarks use 'mlp')")
-        else:
-            raise NotImplementedError(f"Head '{self.head_type}' unknown. Must be one of: 'mlp', "
-                                      f"'fully_convolutional', 'multihead_attention_pooling'")
-
-        for m in self.modules():                                                   # mn/model.py:199-210
-            if isinstance(m, nn.Conv2d):
-                nn.init.kaiming_normal_(m.weight, mode="fan_out")
-                if m.bias is not None:
-                    nn.init.zeros_(m.bias)
-            elif isinstance(m, (nn.BatchNorm2d, nn.GroupNorm, nn.LayerNorm)):
-                nn.init.ones_(m.weight)
-                nn.init.zeros_(m.bias)
-            elif isinstance(m, nn.Linear):
-                nn.init.normal_(m.weight, 0, 0.01)
-                if m.bias is not None:
-                    nn.init.zeros_(m.bias)
+        self.classifier = mlp_head(6 * last.out_channels, last_channel, num_classes, dropout)
+        reference_init_(self)
         self._engine = None
-        # 'fp32' keeps activations in fp32 (tf32 tensor-core / exact fp32 CUDA-core math, logits within 1e-3 of
-        # the reference); 'bf16' stores activations in bf16.  See DESIGN.md section "precision modes".
+        # 'fp32' keeps activations in fp32 (tensor-core bf16x3 / exact fp32 CUDA-core math, logits within 1e-3 of
+        # the reference); 'bf16' stores activations in bf16.  See DESIGN.md section 3.
         self.precision = kwargs.get("precision", "fp32")
 
     def engine(self):
@@ -117,9 +83,7 @@ class MN(nn.Module):
 
     def _forward_impl(self, x: Tensor, return_fmaps: bool = False):
         logits, features, fmaps = self.engine().forward(x, return_fmaps=return_fmaps)
-        if return_fmaps:
-            return logits, fmaps
-        return logits, features
+        return (logits, fmaps) if return_fmaps else (logits, features)
 
     def forward(self, x: Tensor):
         return self._forward_impl(x)
@@ -127,30 +91,10 @@ class MN(nn.Module):
 
 def _mobilenet_v3_conf(width_mult: float = 1.0, reduced_tail: bool = False, dilated: bool = False,
                        strides: Tuple[int, ...] = (2, 2, 2, 2), **kwargs: Any):
-    """The 15-row MobileNetV3-large table (mn/model.py:237-271)."""
-    div = 2 if reduced_tail else 1
-    dil = 2 if dilated else 1
-    rows = [
-        # in, k, exp, out, se, act, stride, dilation
-        (16, 3, 16, 16, False, "RE", 1, 1),
-        (16, 3, 64, 24, False, "RE", strides[0], 1),
-        (24, 3, 72, 24, False, "RE", 1, 1),
-        (24, 5, 72, 40, True, "RE", strides[1], 1),
-        (40, 5, 120, 40, True, "RE", 1, 1),
-        (40, 5, 120, 40, True, "RE", 1, 1),
-        (40, 3, 240, 80, False, "HS", strides[2], 1),
-        (80, 3, 200, 80, False, "HS", 1, 1),
-        (80, 3, 184, 80, False, "HS", 1, 1),
-        (80, 3, 184, 80, False, "HS", 1, 1),
-        (80, 3, 480, 112, True, "HS", 1, 1),
-        (112, 3, 672, 112, True, "HS", 1, 1),
-        (112, 5, 672, 160 // div, True, "HS", strides[3], dil),
-        (160 // div, 5, 960 // div, 160 // div, True, "HS", 1, dil),
-        (160 // div, 5, 960 // div, 160 // div, True, "HS", 1, dil),
-    ]
-    setting = [InvertedResidualConfig(*r, width_mult=width_mult) for r in rows]
-    last_channel = InvertedResidualConfig.adjust_channels(1280 // div, width_mult)
-    return setting, last_channel
+    """15 block configs + classifier width (reference models/mn/model.py:237-271)."""
+    rows, last = v3_large_rows(strides, reduced_tail, dilated)
+    setting = [InvertedResidualConfig(*row, width_mult=width_mult) for row in rows]
+    return setting, InvertedResidualConfig.adjust_channels(last, width_mult)
 
 
 def _mobilenet_v3(inverted_residual_setting, last_channel, pretrained_name, **kwargs):
