@@ -40,6 +40,7 @@ def parse():
                     help="train: the headline training step; eval: mel + forward only (BASELINE.json configs[1])")
     ap.add_argument("--cpu-baseline-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -260,7 +261,7 @@ def run_ours(args):
     with contextlib.redirect_stdout(io.StringIO()):
         model = synth_state_(get_model(width_mult=width, precision=args.precision, verbose=False), seed=7).to(dev)
         mel = AugmentMelSTFT(freqm=0, timem=0).to(dev)          # ex_audioset.py defaults: freqm = timem = 0
-    trainer = AudioSetTrainer(model, mel, lr=8e-4, kd_lambda=0.1, mixup_alpha=0.3)
+    trainer = AudioSetTrainer(model, mel, lr=8e-4, kd_lambda=0.1, mixup_alpha=0.3, cuda_graph=not args.no_graph)
     if args.mode == "eval":
         model.eval()
         mel.eval()
@@ -286,7 +287,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (also finds the dominant kernel for the roofline figure)
+    # ---- warm-up, eager: also finds the dominant kernel for the roofline figure and counts launches per step
+    use_graph = getattr(trainer, "cuda_graph", False)
+    if use_graph:
+        trainer.cuda_graph = False
     for _ in range(max(args.warmup - 1, 2)):
         trainer.step(wave, y, teacher)
     torch.cuda.synchronize()
@@ -298,15 +302,22 @@ def run_ours(args):
     step_launches_before = L.launches
     trainer.step(wave, y, teacher)
     launches_per_step = L.launches - step_launches_before
+    if use_graph:                                   # capture forward + loss + backward once, replay from now on
+        trainer.cuda_graph = True
+        for _ in range(2):
+            trainer.step(wave, y, teacher)
+    torch.cuda.synchronize()
 
     # ---- timed region: device-resident inputs
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks, KernelTimer(L, only={top}) as kt2:
+    with ClockSampler(local) as clocks:
+        h0 = time.perf_counter()
         e0.record()
         for _ in range(args.steps):
             loss = trainer.step(wave, y, teacher)
         e1.record()
+        host_ms = (time.perf_counter() - h0) * 1e3 / args.steps      # time the host needs to ENQUEUE one step
         barrier()
     ms = e0.elapsed_time(e1)
     if world > 1:
@@ -314,6 +325,17 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- per-launch timing of the dominant kernel: the same K steps once more, launched eagerly with CUDA events
+    # around every launch of that kernel (inside a replayed graph there is no host call to bracket)
+    if use_graph:
+        trainer.cuda_graph = False
+    with KernelTimer(L, only={top}) as kt2:
+        for _ in range(args.steps):
+            trainer.step(wave, y, teacher)
+        torch.cuda.synchronize()
+    if use_graph:
+        trainer.cuda_graph = True
     top_ms, top_n, top_bytes, bytes_ok = kt2.table()[top]
 
     # ---- end to end: pinned host buffers -> H2D -> step -> D2H loss, every step
@@ -357,11 +379,11 @@ def run_ours(args):
                                     f"(ex_audioset.py:135-199), batch {B}/GPU, 10 s @ 32 kHz clips") if args.mode == "train"
                        else f"{args.model}_as mel + eval forward (inference.py:51-53), batch {B}/GPU, 10 s @ 32 kHz clips",
                        "model": f"{args.model}_as", "global_batch": B * world, "parallelism": f"dp{world}",
-                       "precision_mode": args.precision,
+                       "precision_mode": args.precision, "cuda_graph": (not args.no_graph) and args.mode == "train",
                        "l2": "inputs (waveforms %.0f MB/GPU) exceed L2; no explicit flush" % (wave.numel() * 4 / 1e6)},
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches": launches_per_step * args.steps, "host_enqueue_ms_per_step": host_ms,
             "clocks": clocks.summary(),
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None,
@@ -370,6 +392,8 @@ def run_ours(args):
                          "traffic_source": NCU_TRAFFIC[top]["capture"] + " (dram/algorithmic ratio of the captured launch x "
                          "this run's algorithmic bytes per launch)" if top in NCU_TRAFFIC else None,
                          "peak_source": peak_src,
+                         "timing": "CUDA events around every launch of this kernel over the same K steps, launched eagerly right "
+                                   "after the graph-replayed timed region" if use_graph else "CUDA events inside the timed region",
                          "launches_timed": top_n, "avg_launch_ms": top_ms / max(top_n, 1),
                          "algorithmic_bytes_per_launch": top_bytes / max(top_n, 1) if bytes_ok else None},
             "kernel_time_shares": shares,

@@ -41,6 +41,23 @@ class _Layer:
     pass
 
 
+class _ZeroPool:
+    """fp64 accumulators for BatchNorm statistics, carved from chunks that are zeroed with ONE fill each
+    (a training step needs ~100 small zeroed buffers; one launch per buffer showed up as 250 tiny kernels)."""
+
+    def __init__(self, chunk=1 << 16):
+        self.chunk, self.buf, self.off = chunk, None, 0
+
+    def take(self, rows, cols, dev):
+        n = rows * cols
+        if self.buf is None or self.off + n > self.buf.numel() or self.buf.device != dev:
+            self.buf = torch.zeros(max(self.chunk, n), device=dev, dtype=torch.float64)
+            self.off = 0
+        v = self.buf[self.off:self.off + n].view(rows, cols)
+        self.off += n
+        return v
+
+
 class MNEngine:
     def __init__(self, model):
         self.model = model
@@ -50,6 +67,7 @@ class MNEngine:
         self.gemm_impl = os.environ.get("EAT_GEMM", "auto")     # auto | simt (exact-fp32 CUDA cores everywhere)
         self.tc_min_rows = 1024                                  # tiny GEMMs (classifier, SE) stay on CUDA cores
         self._se_scale = {}
+        self._zero_pool = _ZeroPool()
         self._plan()
 
     # ------------------------------------------------------------------ structure
@@ -263,7 +281,7 @@ class MNEngine:
 
     # ------------------------------------------------------------------ training forward
     def _new_stats(self, c, dev):
-        return torch.zeros(2, c, device=dev, dtype=torch.float64)
+        return self._zero_pool.take(2, c, dev)
 
     def _forward_train(self, x, dropout_mask=None):
         """Batch-statistics forward.  Returns (logits, feat, saved) where `saved` holds the raw conv outputs
@@ -276,6 +294,7 @@ class MNEngine:
         B, _, F, T = x.shape
         HS = ACT["hswish"]
         S = {"x": x, "B": B, "F": F, "T": T, "blocks": []}
+        self._zero_pool = _ZeroPool()
 
         conv, bn = self.stem[0], self.stem[1]
         s0 = conv.stride[0]
@@ -403,7 +422,7 @@ class MNEngine:
         L = lib()
         st = _stream()
         code = self.dcode if code is None else code
-        s = torch.zeros(2, C, device=dev, dtype=torch.float64)
+        s = self._zero_pool.take(2, C, dev)
         L.bn_bwd_reduce(_ptr(gA), _ptr(gate), _ptr(dpool), z.data_ptr(), sc[0].data_ptr(), sc[1].data_ptr(),
                         sv[0].data_ptr(), sv[1].data_ptr(), act, code, B, P, C, s[0].data_ptr(), s[1].data_ptr(), st)
         coef = torch.empty(2, C, device=dev, dtype=torch.float32)
@@ -481,6 +500,7 @@ class MNEngine:
         td, dc = self.tdtype, self.dcode
         B = S["B"]
         HS = ACT["hswish"]
+        self._zero_pool = _ZeroPool()
         params = self.param_list()
         flat = torch.zeros(sum(p.numel() for p in params), device=dev, dtype=torch.float32)
         G, off = {}, 0

@@ -1,0 +1,7 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -12 | cut -c1-300
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_v10_fp32_b256.json | cut -c1-2100
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --batch 128 2>&1 | tail -1 | tee gpurun_out/bench_v10_fp32_b128.json | cut -c1-600
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --batch 64 2>&1 | tail -1 | cut -c1-400

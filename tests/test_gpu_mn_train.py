@@ -68,3 +68,42 @@ def test_mn_train_bf16_runs_and_is_close():
     tot = sum(p.grad.double().pow(2).sum().item() for p in params.values()) ** 0.5
     ref = float(np.sqrt((g["grad_norm"] ** 2).sum()))
     assert abs(tot - ref) < 0.1 * ref
+
+
+def test_trainer_cuda_graph_matches_eager_steps():
+    """AudioSetTrainer with CUDA-graph replay computes the same steps as the eager trainer.  lr = 0 keeps the
+    parameters fixed (Adam turns fp32 summation-order noise on near-zero gradients into +-lr moves, which would make
+    a parameter comparison meaningless), so losses, the flat gradient arena and the BatchNorm buffers after three
+    steps with different mixup draws must agree; the capture warm-up must not count as training steps."""
+    import contextlib
+    import io
+    from efficientat_b200.models.preprocess import AugmentMelSTFT
+    from efficientat_b200.synth import synth_labels, synth_waveform
+    from efficientat_b200.train import AudioSetTrainer
+
+    def run(graph):
+        model = build_model("mn04").cuda()
+        with contextlib.redirect_stdout(io.StringIO()):
+            mel = AugmentMelSTFT(freqm=0, timem=0, fmin_aug_range=1, fmax_aug_range=1).cuda()
+        model.classifier[4].p = 0.0
+        model.engine().dropout_p = 0.0
+        tr = AudioSetTrainer(model, mel, lr=0.0, mixup_alpha=0.3, cuda_graph=graph)
+        wave = synth_waveform(4, 32000, seed=3).cuda()
+        y = synth_labels(4, 527, seed=4).cuda()
+        teacher = torch.sigmoid(torch.randn(4, 527, generator=torch.Generator().manual_seed(5))).cuda()
+        losses = []
+        for i in range(3):
+            perm = torch.randperm(4, generator=torch.Generator().manual_seed(10 + i))
+            lam = torch.rand(4, generator=torch.Generator().manual_seed(20 + i)) * 0.5 + 0.5
+            losses.append(tr.step(wave, y, teacher, perm=perm, lam=lam).cpu())
+        mel.train()
+        _, flat_g = tr.forward_backward(wave, y, teacher, perm, lam)
+        return model, torch.stack(losses), flat_g.clone()
+
+    m_e, l_e, g_e = run(False)
+    m_g, l_g, g_g = run(True)
+    assert torch.allclose(l_e, l_g, rtol=1e-5, atol=1e-8), (l_e, l_g)
+    assert (g_e - g_g).abs().max() <= 1e-3 * g_e.abs().max(), ((g_e - g_g).abs().max(), g_e.abs().max())
+    for (n, p), (_, q) in zip(m_e.named_buffers(), m_g.named_buffers()):
+        assert torch.allclose(p.float(), q.float(), rtol=1e-4, atol=1e-6), n
+    assert int(dict(m_g.named_buffers())["features.0.1.num_batches_tracked"]) == 4     # 3 steps + the last call
