@@ -5,6 +5,8 @@
 //   apply  : dz = gamma*invstd * (dy - s1/M - xhat * s2/M)
 // where the upstream gradient may be composed on the fly, g = gA * gate[b,c] + dpool[b,c]
 // (squeeze-excitation gate and the gradient of a spatial mean), so those products are never stored.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -561,6 +563,8 @@ int eat_dw_conv_dgrad(const void* dz, const float* wt, long long wt_bstride, con
                       int F, int T, int C, int k, int stride, cudaStream_t st) {
   if (B == 0) return EAT_OK;
   if (stride == 1 && (k == 3 || k == 5)) return eat_dw_conv_dgrad_s1(dz, wt, wt_bstride, res, din, dtype, B, F, T, C, k, st);
+  static const int impl = [] { const char* e = getenv("EAT_DW_IMPL"); return (e && e[0] == 'o') ? 0 : 1; }();   // dev switch: "old"
+  if (impl == 1 && stride == 2 && (k == 3 || k == 5)) return dw_dgrad2_slide_launch(dz, wt, wt_bstride, res, din, dtype, B, F, T, C, k, st);
   InXform xf{nullptr, nullptr, nullptr, 0, 0};
   if (dtype == EAT_BF16) return launch_dw_bwd<__nv_bfloat16>(0, dz, wt, nullptr, xf, res, din, nullptr, B, F, T, C, k, stride, st, wt_bstride);
   return launch_dw_bwd<float>(0, dz, wt, nullptr, xf, res, din, nullptr, B, F, T, C, k, stride, st, wt_bstride);
@@ -571,6 +575,9 @@ int eat_dw_conv_wgrad(const void* dz, const void* in, const float* in_scale, con
                       cudaStream_t st) {
   if (B == 0) return EAT_OK;
   InXform xf{in_scale, in_shift, nullptr, in_act, 0};
+  static const int impl = [] { const char* e = getenv("EAT_DW_IMPL"); return (e && e[0] == 'o') ? 0 : 1; }();   // dev switch: "old"
+  if (impl == 1 && k == 3 && (stride == 1 || stride == 2))
+    return dw_wgrad_slide_launch(dz, in, xf, dw, dw_bstride, dtype, B, F, T, C, k, stride, st);
   if (dtype == EAT_BF16) return launch_dw_bwd<__nv_bfloat16>(1, dz, nullptr, in, xf, nullptr, nullptr, dw, B, F, T, C, k, stride, st, 0, dw_bstride);
   return launch_dw_bwd<float>(1, dz, nullptr, in, xf, nullptr, nullptr, dw, B, F, T, C, k, stride, st, 0, dw_bstride);
 }

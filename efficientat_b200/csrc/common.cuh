@@ -79,6 +79,26 @@ struct InXform {
   int rows_per_sample;   // F*T of the tensor the gate indexes (rows -> sample index)
 };
 
+struct DyEpi {
+  const float* theta;    // [B, C, 4] sigmoid(coef_net(h_c)) or nullptr
+  const float* lam;      // [4] lambdas
+  const float* init;     // [4] init_v
+  const float* ca_f;     // [B, Fo, C] sigmoid(g_cf) or nullptr
+  const float* ca_t;     // [B, To, C] sigmoid(g_ct)
+  long long wt_bstride;  // floats between the weight tables of consecutive samples (0: shared weights)
+};
+
+// sliding-window depthwise convolution (dw_slide.cu); same contract as launch_dw in conv_kernels.cu
+int dw_slide_launch(const void* in, const float* wt, void* out, int dtype, int B, int F, int Tn, int C, int k, int stride,
+                    InXform xf, const float* scale, const float* shift, int act, const void* res, int flip, float* pool,
+                    double* ssum, double* ssq, cudaStream_t st, DyEpi dy);
+
+int dw_wgrad_slide_launch(const void* dz, const void* in, InXform xf, float* dw, long long dw_bstride, int dtype, int B,
+                          int F, int Tn, int C, int k, int stride, cudaStream_t st);
+
+int dw_dgrad2_slide_launch(const void* dz, const float* wt, long long wt_bstride, const void* res, void* din, int dtype,
+                           int B, int F, int Tn, int C, int k, cudaStream_t st);
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

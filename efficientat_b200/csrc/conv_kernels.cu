@@ -6,6 +6,8 @@
 // statistics (training).  Reference semantics: torchvision ConvNormActivation as used at
 // models/mn/model.py:125-133 and models/mn/block_types.py:140-170; SqueezeExcitation
 // models/mn/block_types.py:72-83.
+#include <cstdlib>
+
 #include "common.cuh"
 #include <stdlib.h>
 
@@ -120,14 +122,6 @@ __global__ void __launch_bounds__(kThreads) stem_kernel(
 // grid = (chunks, B) so per-(sample, channel) pooling stays inside a CTA column.
 // DyMN extras for the depthwise kernel (reference models/dymn/dy_block.py): per-sample mixed weights
 // (DynamicConv :111-127), DyReLU-B (:172-188) and coordinate attention (:195-201) as a register-resident epilogue.
-struct DyEpi {
-  const float* theta;    // [B, C, 4] sigmoid(coef_net(h_c)) or nullptr
-  const float* lam;      // [4] lambdas
-  const float* init;     // [4] init_v
-  const float* ca_f;     // [B, Fo, C] sigmoid(g_cf) or nullptr
-  const float* ca_t;     // [B, To, C] sigmoid(g_ct)
-  long long wt_bstride;  // floats between the weight tables of consecutive samples (0: shared weights)
-};
 
 // MODE 0: training forward (optional input BN+act, raw output + batch statistics)
 // MODE 1: eval forward (folded BN + act epilogue, SE pooling, DyMN epilogue)     MODE 2: stride-1 data gradient
@@ -640,6 +634,13 @@ int launch_dw(const T* in, const float* wt, T* out, int B, int F, int Tn, int C,
   if (C % V != 0) { eat_set_error("dw conv: channels must be a multiple of the vector width"); return EAT_ERR_ARG; }
   const int pad = (k - 1) / 2;
   const int Fo = (F + 2 * pad - k) / stride + 1, To = (Tn + 2 * pad - k) / stride + 1;
+  static const int impl = [] { const char* e = getenv("EAT_DW_IMPL"); return (e && e[0] == 'o') ? 0 : 1; }();   // dev switch: "old"
+  const int mode_ = (scale != nullptr || pool != nullptr || dy.theta != nullptr || dy.ca_f != nullptr) ? 1 : ((flip || res != nullptr) ? 2 : 0);
+  // sliding-window kernel (dw_slide.cu) for every 3x3 case and the 5x5 training forward; the 5x5 eval / data-gradient
+  // cases stay on the shared-memory tile kernel below (measured faster there: profiles/README.md)
+  if (impl == 1 && (stride == 1 || stride == 2) && (k == 3 || (k == 5 && mode_ == 0)) && !(mode_ == 2 && stride != 1))
+    return dw_slide_launch(in, wt, out, V == 8 ? EAT_BF16 : EAT_F32, B, F, Tn, C, k, stride, xf, scale, shift, act, res, flip,
+                           pool, ssum, ssq, st, dy);
   if (k == 3 || k == 5) {
     const bool tiled = (k == 5);     // measured (profiles/r01_dw_microbench*): smem tiling pays for 5x5, not for 3x3
     if (!tiled) {
