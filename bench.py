@@ -370,6 +370,10 @@ def run_ours(args):
         achieved = (top_bytes / 1e9) / (top_ms * 1e-3) if (bytes_ok and top_ms > 0) else None
         shares = {k: round(v[0] / sum(x[0] for x in prof.values()), 4) for k, v in
                   sorted(prof.items(), key=lambda kv: -kv[1][0])[:8]}
+        if os.environ.get("EAT_BENCH_KERNELS"):      # full per-entry-point table (ms per step, launches per step) on stderr
+            for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+                print(f"  {k:28s} {v[0] / args.steps:8.3f} ms/step {v[1] // args.steps:5d} launches"
+                      + (f" {v[2] / 1e6 / v[0]:8.0f} GB/s" if v[3] and v[0] > 0 else ""), file=sys.stderr)
         line = {
             "metric": METRIC if (args.mode == "train" and args.model == "mn10") else
             f"clips/sec (10s@32kHz) {args.model}_as {'fwd+bwd' if args.mode == 'train' else 'fwd'}", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,

@@ -120,9 +120,19 @@ __device__ __forceinline__ float act_sel(float v, int act) {     // branch-free 
   return act == EAT_ACT_HSWISH ? h : (act == EAT_ACT_RELU ? r : v);
 }
 
+// input transform applied while the A operand is staged: XACT -1 none, 0 affine, 1 affine + ReLU, 2 affine + Hardswish,
+// 3 affine + run-time activation code (only instantiated for the fused-epilogue variants, where it is rare)
+template <int XACT>
+__device__ __forceinline__ float act_in(float v, int act) {
+  if (XACT == 1) return fmaxf(v, 0.f);
+  if (XACT == 2) return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+  if (XACT == 3) return act_sel(v, act);
+  return v;
+}
+
 // T: activation storage type.  NP = 1: operands rounded to bf16 (bf16 mode); NP = 2: hi/lo split (fp32 mode).
 // EPI: 0 raw output (+ statistics), 1 affine, 2 affine + ReLU, 3 affine + Hardswish (each + optional residual)
-template <typename T, int NP, int STAGES, int BN_MAX, bool DYN, int EPI>
+template <typename T, int NP, int STAGES, int BN_MAX, bool DYN, int EPI, int XACT>
 __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
   constexpr bool AFF = EPI != 0;  // 17 warps are allocated as 20: 96 registers/thread is the ceiling
   constexpr int B_TILE_BYTES = BN_MAX * 128;
@@ -165,11 +175,33 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
     const T* __restrict__ A = reinterpret_cast<const T*>(p.A);
     const int rps = p.xf.rows_per_sample;
     int it = 0;                                                    // global (tile, k-block) counter of this CTA
+    // the weight tile of a stage is still valid when the tile that used the stage last had the same (N tile, k-block,
+    // sample): true for STAGES / k_blocks tiles back whenever k_blocks divides STAGES (every K <= 64 * STAGES layer)
+    const int back = (p.k_blocks <= STAGES && STAGES % p.k_blocks == 0) ? STAGES / p.k_blocks : 0;
+    int h0 = -1, h1 = -1, h2 = -1;                                 // keys of the previous three tiles of this CTA
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;       // m fastest: a CTA stays on one N tile
       long long m0, m_lim;
       int bsample;
       tile_rows<DYN>(p, mt, m0, m_lim, bsample);
+      if (threadIdx.x == 0) {
+        // L2 prefetch of the A rows this CTA stages two tiles from now (a [rows, K] tile is one contiguous range)
+        for (int ahead = (t == (int)blockIdx.x ? 1 : 2); ahead <= 2; ++ahead) {
+          const int t2 = t + ahead * gridDim.x;
+          if (t2 < total_tiles) {
+            const int nt2 = t2 / p.m_tiles;
+            long long m2, lim2;
+            int b2;
+            tile_rows<DYN>(p, t2 - nt2 * p.m_tiles, m2, lim2, b2);
+            const long long rows2 = lim2 - m2 < BM ? lim2 - m2 : BM;
+            l2_prefetch(A + m2 * (long long)K, (uint32_t)(rows2 * K * (long long)sizeof(T)));
+          }
+        }
+      }
+      const int key = DYN ? (nt * 65536 + bsample) : nt;
+      const int hist = back == 1 ? h0 : (back == 2 ? h1 : (back == 3 ? h2 : -1));
+      const bool b_resident = (back != 0) && (hist == key);
+      h2 = h1; h1 = h0; h0 = key;
       float datt[4] = {0.f, 0.f, 0.f, 0.f};
       if (DYN) {
 #pragma unroll
@@ -196,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
         const bool kok = kc < nch && k < K;                                // k >= K inside nch: zero fill
         const bool kact = kc < nch;
         float isc[8], ish[8];
-        if (p.xf.scale != nullptr && kok) {
+        if (XACT >= 0 && kok) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) { isc[j] = __ldg(p.xf.scale + k + j); ish[j] = __ldg(p.xf.shift + k + j); }
         }
@@ -222,12 +254,12 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
             const int j = j0 + i;
             if (j >= nrow || !kact) continue;
             const int row = r0 + j * rstep;
-            if (p.xf.scale != nullptr || p.xf.gate != nullptr) {
+            if (XACT >= 0 || p.xf.gate != nullptr) {
               const bool ok = kok && (full || m0 + row < m_lim);
               if (ok) {
-                if (p.xf.scale != nullptr) {
+                if (XACT >= 0) {
 #pragma unroll
-                  for (int q = 0; q < 8; ++q) av[i][q] = act_sel(fmaf(av[i][q], isc[q], ish[q]), p.xf.act);
+                  for (int q = 0; q < 8; ++q) av[i][q] = act_in<XACT>(fmaf(av[i][q], isc[q], ish[q]), p.xf.act);
                 }
                 if (p.xf.gate != nullptr) {
                   const int rel = off0 + row;
@@ -242,8 +274,8 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
             store_chunk<NP>(sA_hi, sA_lo, swz(row, kc), av[i]);
           }
         }
-        // ---- B: BN rows (output channels) of the fp32 weight matrix, batches of 4 rows
-        for (int rb = r0; rb < BN; rb += 4 * rstep) {
+        // ---- B: BN rows (output channels) of the fp32 weight matrix, batches of 4 rows; skipped while resident
+        for (int rb = b_resident ? BN : r0; rb < BN; rb += 4 * rstep) {
           float wv[4][8];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -356,6 +388,16 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
         cur_nt = nt;
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
+      if (AFF && R != nullptr && p.n_tiles == 1 && etid == 0) {
+        const int t2 = t + gridDim.x;                  // residual rows of this CTA's next tile (contiguous: BN == N)
+        if (t2 < total_tiles) {
+          long long m2, lim2;
+          int b2;
+          tile_rows<DYN>(p, t2, m2, lim2, b2);
+          const long long rows2 = lim2 - m2 < BM ? lim2 - m2 : BM;
+          l2_prefetch(R + m2 * (long long)N, (uint32_t)(rows2 * N * (long long)sizeof(T)));
+        }
+      }
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN_MAX;
@@ -455,8 +497,8 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
   }
 }
 
-template <typename T, int NP, int STAGES, int BN_MAX, bool DYN, int EPI>
-int launch_tc_aff(const TcParams& p0, cudaStream_t st) {
+template <typename T, int NP, int STAGES, int BN_MAX, bool DYN, int EPI, int XACT>
+int launch_tc_x(const TcParams& p0, cudaStream_t st) {
   TcParams p = p0;
   p.n_tiles = ceil_div(p.N, BN_MAX);
   p.BN = ceil_div(ceil_div(p.N, p.n_tiles), 16) * 16;
@@ -475,7 +517,7 @@ int launch_tc_aff(const TcParams& p0, cudaStream_t st) {
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(pw_tc_kernel<T, NP, STAGES, BN_MAX, DYN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(pw_tc_kernel<T, NP, STAGES, BN_MAX, DYN, EPI, XACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { eat_set_error(cudaGetErrorString(e)); return EAT_ERR_CUDA; }
     attr_done = true;
   }
@@ -484,9 +526,26 @@ int launch_tc_aff(const TcParams& p0, cudaStream_t st) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < sms ? tiles : sms;
-  pw_tc_kernel<T, NP, STAGES, BN_MAX, DYN, EPI><<<grid, kThreads, smem, st>>>(p);
+  pw_tc_kernel<T, NP, STAGES, BN_MAX, DYN, EPI, XACT><<<grid, kThreads, smem, st>>>(p);
   EAT_CHECK_LAUNCH();
   return EAT_OK;
+}
+
+// instantiated input transforms: the raw-output (training / data-gradient) kernel gets compile-time activations, the
+// fused-epilogue (eval) kernels normally see already-activated inputs and keep one run-time variant for the rest
+template <typename T, int NP, int STAGES, int BN_MAX, bool DYN, int EPI>
+int launch_tc_aff(const TcParams& p, cudaStream_t st) {
+  if (p.xf.scale == nullptr) return launch_tc_x<T, NP, STAGES, BN_MAX, DYN, EPI, -1>(p, st);
+  if constexpr (DYN) {
+    eat_set_error("pw_tc_dyn: input BatchNorm/activation on load is not instantiated for DynamicConv");
+    return EAT_ERR_UNSUPPORTED;
+  } else if constexpr (EPI == 0) {
+    if (p.xf.act == EAT_ACT_RELU) return launch_tc_x<T, NP, STAGES, BN_MAX, DYN, EPI, 1>(p, st);
+    if (p.xf.act == EAT_ACT_HSWISH) return launch_tc_x<T, NP, STAGES, BN_MAX, DYN, EPI, 2>(p, st);
+    return launch_tc_x<T, NP, STAGES, BN_MAX, DYN, EPI, 0>(p, st);
+  } else {
+    return launch_tc_x<T, NP, STAGES, BN_MAX, DYN, EPI, 3>(p, st);
+  }
 }
 
 template <typename T, int NP, int STAGES, int BN_MAX, bool DYN>

@@ -131,6 +131,17 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(WgParams p) {
       unsigned char* sA_hi = sG_hi + NP * G_TILE;
       unsigned char* sA_lo = sA_hi + A_TILE;
       const long long mb = m_begin + (long long)blk * MB;
+      if (gtid == 0) {
+        // L2 prefetch of the rows this group stages two of its blocks from now (whole rows: contiguous ranges)
+        for (int ahead = (blk == grp ? 2 : 4); ahead <= 4; ahead += 2) {
+          const long long m2 = mb + (long long)ahead * MB;
+          if (m2 < m_end) {
+            const long long rows2 = m_end - m2 < MB ? m_end - m2 : MB;
+            l2_prefetch(G + m2 * N, (uint32_t)(rows2 * N * (long long)sizeof(T)));
+            l2_prefetch(A + m2 * K, (uint32_t)(rows2 * K * (long long)sizeof(T)));
+          }
+        }
+      }
       if (gact) {
         for (int rb = rG0; rb < MB; rb += 4 * rGs) {
           float v[4][8];
