@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(WgParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES), bar_tfull = smem_u32(bars + 2 * STAGES);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, kGroupThreads); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, kGroupThreads / 32); mbar_init(bar_empty + 8 * s, 1); }   // one arrival per warp
     mbar_init(bar_tfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -201,7 +201,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(WgParams p) {
         }
       }
       fence_proxy_async();
-      mbar_arrive(bar_full + 8 * stage);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * stage);
     }
   } else if (warp == kMmaWarp) {
     // ================================================================= MMA issuer

@@ -17,6 +17,7 @@ ap.add_argument("--impl", default="pw_tc_fwd")
 ap.add_argument("--dtype", default="fp32")
 ap.add_argument("--only", type=int, default=-1)
 ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--raw", action="store_true", help="no input transform, no epilogue, no statistics (data-gradient shape)")
 ap.add_argument("--train", action="store_true", help="training-mode variant: raw output + statistics, BN+act on load")
 a = ap.parse_args()
 L = lib()
@@ -40,7 +41,9 @@ for i, (rows, K, N, res, xf) in enumerate(LAYERS):
     gate = torch.rand(a.batch, K, device="cuda") if xf else None
     stats = torch.zeros(2, N, device="cuda", dtype=torch.float64)
     p = lambda t: 0 if t is None else t.data_ptr()
-    if a.train:
+    if a.raw:
+        args = (A.data_ptr(), code, W.data_ptr(), 0, C.data_ptr(), code, M, N, K, 0, 0, 0, 0, rows, 0, 0, 0, 0, 0, 0, st)
+    elif a.train:
         args = (A.data_ptr(), code, W.data_ptr(), 0, C.data_ptr(), code, M, N, K, isc[0].data_ptr(), isc[1].data_ptr(), 2,
                 p(gate), rows, 0, 0, 0, 0, stats[0].data_ptr(), stats[1].data_ptr(), st)
     else:
@@ -56,7 +59,7 @@ for i, (rows, K, N, res, xf) in enumerate(LAYERS):
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     ms = sorted(ts)[len(ts) // 2]
-    nbytes = M * K * es + M * N * es * (2 if (res and not a.train) else 1) + N * K * 4
+    nbytes = M * K * es + M * N * es * (2 if (res and not a.train and not a.raw) else 1) + N * K * 4
     tot_t += ms; tot_b += nbytes
     print(f"{i:2d} M={M:8d} K={K:4d} N={N:4d} res={res} xf={xf}  {ms*1e3:8.1f} us  {nbytes/ms/1e6:8.1f} GB/s  "
           f"{2*M*N*K/ms/1e9:8.2f} TFLOP/s", flush=True)
