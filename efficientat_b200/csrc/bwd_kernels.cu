@@ -576,7 +576,7 @@ int eat_dw_conv_wgrad(const void* dz, const void* in, const float* in_scale, con
   if (B == 0) return EAT_OK;
   InXform xf{in_scale, in_shift, nullptr, in_act, 0};
   static const int impl = [] { const char* e = getenv("EAT_DW_IMPL"); return (e && e[0] == 'o') ? 0 : 1; }();   // dev switch: "old"
-  if (impl == 1 && k == 3 && (stride == 1 || stride == 2))
+  if (impl == 1 && (k == 3 || (k == 5 && dtype != EAT_BF16)) && (stride == 1 || stride == 2))
     return dw_wgrad_slide_launch(dz, in, xf, dw, dw_bstride, dtype, B, F, T, C, k, stride, st);
   if (dtype == EAT_BF16) return launch_dw_bwd<__nv_bfloat16>(1, dz, nullptr, in, xf, nullptr, nullptr, dw, B, F, T, C, k, stride, st, 0, dw_bstride);
   return launch_dw_bwd<float>(1, dz, nullptr, in, xf, nullptr, nullptr, dw, B, F, T, C, k, stride, st, 0, dw_bstride);

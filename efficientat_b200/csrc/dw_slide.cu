@@ -31,6 +31,7 @@ __device__ __forceinline__ float xact(float v) {
   return v;
 }
 
+
 struct SlideArgs {
   const void* in;
   const float* wt;
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(kST, MINB) dw_slide_kernel(const SlideArgs a) 
   if (slot < ppb) {
     const int c0 = (cv0 + cvl) * V;
     const float* wl = s_w + cvl * V;
+
     float isc[V], ish[V];
     if (kXf) {
 #pragma unroll
@@ -385,6 +387,22 @@ int launch_slide(SlideArgs a, int B, int k, int stride, int mode, int xact_code,
 // Same walk as the forward kernel: a thread keeps the 9 tap accumulators of its channel vector in registers for
 // its whole life (all strips, segments and samples it visits), slides a window of the L = ceil(3/S) most recent dz
 // rows, and loads + transforms every input row once.  One shared-memory / global atomic flush per CTA at the end.
+// V channels per thread as one vector load: the 5x5 weight gradient keeps 25 tap accumulators per channel, so it
+// takes 2 fp32 channels (8-byte loads) per thread instead of 4 to stay in registers
+template <typename T, int VW> struct VecW;
+template <> struct VecW<float, 4> {
+  __device__ __forceinline__ static void load(const float* p, float (&v)[4]) { Vec<float>::load(p, v); }
+};
+template <> struct VecW<float, 2> {
+  __device__ __forceinline__ static void load(const float* p, float (&v)[2]) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    v[0] = t.x; v[1] = t.y;
+  }
+};
+template <> struct VecW<__nv_bfloat16, 8> {
+  __device__ __forceinline__ static void load(const __nv_bfloat16* p, float (&v)[8]) { Vec<__nv_bfloat16>::load(p, v); }
+};
+
 struct WgArgs {
   const void* dz;
   const void* in;
@@ -397,10 +415,9 @@ struct WgArgs {
   const float* xshift;
 };
 
-template <typename T, int S, int P, int XACT, int MINB>
+template <typename T, int K, int S, int P, int V, int XACT, int MINB>
 __global__ void __launch_bounds__(kST, MINB) dw_wgrad_slide_kernel(const WgArgs a) {
-  constexpr int K = 3, KK = 9, PAD = 1;
-  constexpr int V = Vec<T>::N;
+  constexpr int KK = K * K, PAD = (K - 1) / 2;
   constexpr int NIN = (P - 1) * S + K;
   constexpr int L = (K + S - 1) / S;
   constexpr bool kXf = XACT >= 0;
@@ -466,7 +483,7 @@ __global__ void __launch_bounds__(kST, MINB) dw_wgrad_slide_kernel(const WgArgs 
           float v[NIN][V];
 #pragma unroll
           for (int j = 0; j < NIN; ++j) {
-            if ((cmask >> j) & 1u) Vec<T>::load(rp + (size_t)j * C, v[j]);
+            if ((cmask >> j) & 1u) VecW<T, V>::load(rp + (size_t)j * C, v[j]);
             else {
 #pragma unroll
               for (int i = 0; i < V; ++i) v[j][i] = 0.f;
@@ -486,7 +503,7 @@ __global__ void __launch_bounds__(kST, MINB) dw_wgrad_slide_kernel(const WgArgs 
 #pragma unroll
           for (int ky = 0; ky < K; ++ky) {
             if ((ky % S) != PH) continue;
-            const int sl = (S == 1) ? (L - 1 - ky) : (PH == 0 ? (L - 1 - ky / 2) : (L - 1));
+            const int sl = (S == 1) ? (L - 1 - ky) : (PH == 0 ? (L - 1 - ky / 2) : (L - 1 - (ky - 1) / 2));
 #pragma unroll
             for (int kx = 0; kx < K; ++kx)
 #pragma unroll
@@ -512,7 +529,7 @@ __global__ void __launch_bounds__(kST, MINB) dw_wgrad_slide_kernel(const WgArgs 
             const T* gp = dzp + (size_t)n * To * C;
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-              if (to0 + p < To) Vec<T>::load(gp + (size_t)p * C, dzw[L - 1][p]);
+              if (to0 + p < To) VecW<T, V>::load(gp + (size_t)p * C, dzw[L - 1][p]);
               else {
 #pragma unroll
                 for (int i = 0; i < V; ++i) dzw[L - 1][p][i] = 0.f;
@@ -525,7 +542,7 @@ __global__ void __launch_bounds__(kST, MINB) dw_wgrad_slide_kernel(const WgArgs 
               for (int i = 0; i < V; ++i) dzw[L - 1][p][i] = 0.f;
           }
           feed(i0 + n * S, Ph0{});
-          if (S == 2 && n < nrows) feed(i0 + 2 * n + 1, Ph1{});
+          if (S == 2 && n < nrows + (K - 3) / 2) feed(i0 + 2 * n + 1, Ph1{});   // odd kernel rows reach dz rows n .. n - (K-3)/2
         }
       }
     }
@@ -542,33 +559,30 @@ __global__ void __launch_bounds__(kST, MINB) dw_wgrad_slide_kernel(const WgArgs 
   }
 }
 
-template <typename T, int S, int P, int MINB>
+template <typename T, int K, int S, int P, int V, int MINB>
 int launch_wg_act(const WgArgs& a, int xact_code, dim3 grid, size_t smem, cudaStream_t st) {
   switch (xact_code) {
-    case -1: dw_wgrad_slide_kernel<T, S, P, -1, MINB><<<grid, kST, smem, st>>>(a); break;
-    case EAT_ACT_NONE: dw_wgrad_slide_kernel<T, S, P, EAT_ACT_NONE, MINB><<<grid, kST, smem, st>>>(a); break;
-    case EAT_ACT_RELU: dw_wgrad_slide_kernel<T, S, P, EAT_ACT_RELU, MINB><<<grid, kST, smem, st>>>(a); break;
-    case EAT_ACT_HSWISH: dw_wgrad_slide_kernel<T, S, P, EAT_ACT_HSWISH, MINB><<<grid, kST, smem, st>>>(a); break;
+    case -1: dw_wgrad_slide_kernel<T, K, S, P, V, -1, MINB><<<grid, kST, smem, st>>>(a); break;
+    case EAT_ACT_NONE: dw_wgrad_slide_kernel<T, K, S, P, V, EAT_ACT_NONE, MINB><<<grid, kST, smem, st>>>(a); break;
+    case EAT_ACT_RELU: dw_wgrad_slide_kernel<T, K, S, P, V, EAT_ACT_RELU, MINB><<<grid, kST, smem, st>>>(a); break;
+    case EAT_ACT_HSWISH: dw_wgrad_slide_kernel<T, K, S, P, V, EAT_ACT_HSWISH, MINB><<<grid, kST, smem, st>>>(a); break;
     default: eat_set_error("dw wgrad slide: unsupported input activation"); return EAT_ERR_UNSUPPORTED;
   }
   return EAT_OK;
 }
 
-template <typename T>
+// K = 3: 4 fp32 (8 bf16) channels per thread; K = 5 (fp32 only): 2 channels per thread, 25 x 2 tap accumulators
+template <typename T, int K, int V, int P, int MINB>
 int launch_wg_slide(WgArgs a, int stride, int xact_code, cudaStream_t st) {
-  constexpr int V = Vec<T>::N;
-  constexpr bool kF32 = V == 4;
-  constexpr int P = kF32 ? 4 : 1;              // bf16 vectors carry 8 channels: 72 accumulator registers
   const int cv = a.C / V;
-  constexpr int minb = kF32 ? 4 : 3;
   a.per_sample = a.dw_bstride != 0 ? 1 : 0;
-  const SlidePlan pl = plan_slide(a.B, a.Fo, a.To, cv, V, P, stride, 3, minb, a.per_sample != 0);
+  const SlidePlan pl = plan_slide(a.B, a.Fo, a.To, cv, V, P, stride, K, MINB, a.per_sample != 0);
   a.chunks = pl.chunks; a.cvc = pl.cvc; a.seg_rows = pl.seg_rows;
   dim3 grid(pl.chunks * pl.groups, pl.gy);
-  const size_t smem = (size_t)9 * a.cvc * V * sizeof(float);
+  const size_t smem = (size_t)K * K * a.cvc * V * sizeof(float);
   int rc;
-  if (stride == 1) rc = launch_wg_act<T, 1, P, minb>(a, xact_code, grid, smem, st);
-  else rc = launch_wg_act<T, 2, P, minb>(a, xact_code, grid, smem, st);
+  if (stride == 1) rc = launch_wg_act<T, K, 1, P, V, MINB>(a, xact_code, grid, smem, st);
+  else rc = launch_wg_act<T, K, 2, P, V, MINB>(a, xact_code, grid, smem, st);
   if (rc != EAT_OK) return rc;
   EAT_CHECK_LAUNCH();
   return EAT_OK;
@@ -723,7 +737,7 @@ template <typename T>
 int launch_dg2_slide(Dg2Args a, int k, cudaStream_t st) {
   constexpr int V = Vec<T>::N;
   const int cv = a.C / V;
-  const int minb = 4;
+  const int minb = k == 3 ? 4 : 3;
   a.per_sample = a.wt_bstride != 0 ? 1 : 0;
   const int pairs = (a.F + 1) / 2;
   const SlidePlan pl = plan_slide(a.B, pairs, a.Tn, cv, V, 4, 1, (k + 1) / 2, minb, a.per_sample != 0);
@@ -733,8 +747,8 @@ int launch_dg2_slide(Dg2Args a, int k, cudaStream_t st) {
   if (k == 3) dw_dgrad2_slide_kernel<T, 3, 4><<<grid, kST, smem, st>>>(a);
   else {
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(dw_dgrad2_slide_kernel<T, 5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr = true; }
-    dw_dgrad2_slide_kernel<T, 5, 4><<<grid, kST, smem, st>>>(a);
+    if (!attr) { cudaFuncSetAttribute(dw_dgrad2_slide_kernel<T, 5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr = true; }
+    dw_dgrad2_slide_kernel<T, 5, 3><<<grid, kST, smem, st>>>(a);
   }
   EAT_CHECK_LAUNCH();
   return EAT_OK;
@@ -767,16 +781,21 @@ int dw_wgrad_slide_launch(const void* dz, const void* in, InXform xf, float* dw,
                           int F, int Tn, int C, int k, int stride, cudaStream_t st) {
   const int V = dtype == EAT_BF16 ? 8 : 4;
   if (C % V != 0) { eat_set_error("dw wgrad: channels must be a multiple of the vector width"); return EAT_ERR_ARG; }
-  if (k != 3 || (stride != 1 && stride != 2)) { eat_set_error("dw wgrad slide: 3x3, stride 1 or 2 only"); return EAT_ERR_UNSUPPORTED; }
+  if (!((k == 3 || (k == 5 && dtype != EAT_BF16)) && (stride == 1 || stride == 2))) {
+    eat_set_error("dw wgrad slide: 3x3 (fp32, bf16) or 5x5 (fp32), stride 1 or 2");
+    return EAT_ERR_UNSUPPORTED;
+  }
+  const int pad = (k - 1) / 2;
   WgArgs a;
   a.dz = dz; a.in = in; a.dw = dw; a.dw_bstride = dw_bstride;
   a.B = B; a.F = F; a.Tn = Tn; a.C = C;
-  a.Fo = (F + 2 - 3) / stride + 1;
-  a.To = (Tn + 2 - 3) / stride + 1;
+  a.Fo = (F + 2 * pad - k) / stride + 1;
+  a.To = (Tn + 2 * pad - k) / stride + 1;
   a.xscale = xf.scale; a.xshift = xf.shift;
   const int xact_code = xf.scale != nullptr ? xf.act : -1;
-  if (dtype == EAT_BF16) return launch_wg_slide<__nv_bfloat16>(a, stride, xact_code, st);
-  return launch_wg_slide<float>(a, stride, xact_code, st);
+  if (dtype == EAT_BF16) return launch_wg_slide<__nv_bfloat16, 3, 8, 1, 3>(a, stride, xact_code, st);
+  if (k == 5) return launch_wg_slide<float, 5, 2, 4, 3>(a, stride, xact_code, st);
+  return launch_wg_slide<float, 3, 4, 4, 4>(a, stride, xact_code, st);
 }
 
 int dw_dgrad2_slide_launch(const void* dz, const float* wt, long long wt_bstride, const void* res, void* din, int dtype,

@@ -124,3 +124,4 @@ def test_dw_backward_data_and_weight_gradients(dtype):
         wscale = gw.abs().max().item() + 1e-6
         werr = (dw.double() - gw).abs().max().item()
         assert werr <= (1e-4 if code == 0 else 2e-2) * wscale, ("wgrad", idx, (B, F, T, C, k, s), werr, wscale)
+
