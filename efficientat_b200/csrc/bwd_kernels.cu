@@ -397,8 +397,10 @@ __global__ void __launch_bounds__(kThreads) stem_wgrad_kernel(const T* __restric
     for (int q = 0; q < 9; ++q)
 #pragma unroll
       for (int k = 0; k < V; ++k) acc[q][k] = 0.f;
-    for (long long pix = (long long)blockIdx.x * ppb + slot; pix < npix; pix += (long long)gridDim.x * ppb) {
-      const int to = (int)(pix % To), fo = (int)((pix / To) % Fo), b = (int)(pix / ((long long)To * Fo));
+    const unsigned ppx = (unsigned)To * (unsigned)Fo;       // 32-bit index math: npix < 2^31 is checked by the launcher
+    for (unsigned pix = blockIdx.x * ppb + slot; pix < (unsigned)npix; pix += gridDim.x * ppb) {
+      const unsigned b_ = pix / ppx, rem_ = pix - b_ * ppx;
+      const int fo = (int)(rem_ / (unsigned)To), to = (int)(rem_ - (rem_ / (unsigned)To) * (unsigned)To), b = (int)b_;
       float g[V];
       Vec<T>::load(dz + (size_t)pix * C + cvi * V, g);
 #pragma unroll
@@ -589,6 +591,7 @@ int eat_stem_wgrad(const void* dz, int dtype, const float* x, float* dw, int B, 
   if (C % V != 0 || C / V > kThreads) { eat_set_error("stem wgrad: unsupported channel count"); return EAT_ERR_ARG; }
   const long long npix = (long long)B * Fo * To;
   if (npix == 0) return EAT_OK;
+  if (npix >= (1ll << 31)) { eat_set_error("stem wgrad: B*Fo*To must be below 2^31"); return EAT_ERR_ARG; }
   const int ppb = kThreads / (C / V);
   int grid = (int)min((long long)148 * 4, ceil_div_ll(npix, ppb * 8));
   if (grid < 1) grid = 1;

@@ -72,10 +72,11 @@ __global__ void __launch_bounds__(kThreads) stem_kernel(
 #pragma unroll
   for (int i = 0; i < V; ++i) { lsum[i] = 0.f; lsq[i] = 0.f; }
   if (active) {
-    for (long long pix = (long long)blockIdx.x * ppb + slot; pix < npix; pix += (long long)gridDim.x * ppb) {
-      int to = (int)(pix % To);
-      int fo = (int)((pix / To) % Fo);
-      int b = (int)(pix / ((long long)To * Fo));
+    // 32-bit index math (the launcher guarantees npix < 2^31): three 64-bit div/mod per pixel cost more than the 9 taps
+    const unsigned ppx = (unsigned)To * (unsigned)Fo;
+    for (unsigned pix = blockIdx.x * ppb + slot; pix < (unsigned)npix; pix += gridDim.x * ppb) {
+      const unsigned b_ = pix / ppx, rem_ = pix - b_ * ppx;
+      const int fo = (int)(rem_ / (unsigned)To), to = (int)(rem_ - (rem_ / (unsigned)To) * (unsigned)To), b = (int)b_;
       float acc[V];
 #pragma unroll
       for (int i = 0; i < V; ++i) acc[i] = 0.f;
@@ -706,6 +707,7 @@ int eat_stem_fwd(const float* x, const float* w, void* out, int out_dtype, int B
   if (C % V != 0 || C / V > kThreads) { eat_set_error("stem: unsupported channel count"); return EAT_ERR_ARG; }
   const long long npix = (long long)B * Fo * To;
   if (npix == 0) return EAT_OK;
+  if (npix >= (1ll << 31)) { eat_set_error("stem: B*Fo*To must be below 2^31"); return EAT_ERR_ARG; }
   const int ppb = kThreads / (C / V);
   int grid = grid_for(npix, ppb, 148 * 8);
   size_t smem = (size_t)11 * C * sizeof(float);

@@ -59,8 +59,9 @@ __global__ void __launch_bounds__(kThreads) gemm_nt_kernel(
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < K; k0 += BK) {
-    float av[8];
+  float av[8], bv[4];
+  // global -> registers for the k-block at k0 (input transform applied here); issued one block ahead of the math
+  auto fetch = [&](int k0) {
     const int ka = k0 + a_kc;
     if (a_ok && ka < K) {
       if ((K & 7) == 0) load8<TA>(A + a_m * K + ka, av);
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(kThreads) gemm_nt_kernel(
 #pragma unroll
       for (int i = 0; i < 8; ++i) av[i] = 0.f;
     }
-    float bv[4] = {0.f, 0.f, 0.f, 0.f};
+    bv[0] = bv[1] = bv[2] = bv[3] = 0.f;
     if (!BT) {
       const int kb = k0 + b_kc;
       if (n0 + b_row < N && kb < K) {
@@ -105,6 +106,9 @@ __global__ void __launch_bounds__(kThreads) gemm_nt_kernel(
         }
       }
     }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += BK) {
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 8; ++i) As[a_kc + i][a_row] = av[i];
@@ -115,6 +119,7 @@ __global__ void __launch_bounds__(kThreads) gemm_nt_kernel(
       *reinterpret_cast<float4*>(&Bs[tid >> 4][(tid & 15) * 4]) = make_float4(bv[0], bv[1], bv[2], bv[3]);
     }
     __syncthreads();
+    if (k0 + BK < K) fetch(k0 + BK);          // the next block's loads fly while this block is multiplied
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
