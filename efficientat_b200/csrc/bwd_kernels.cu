@@ -45,11 +45,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(
         dp[k] = dpool != nullptr ? dpool[(size_t)b * C + c0 + k] : 0.f;
         a1[k] = 0.f; a2[k] = 0.f;
       }
-      for (int p = blockIdx.x * ppb + slot; p < P; p += gridDim.x * ppb) {
-        const size_t off = ((size_t)b * P + p) * C + c0;
-        float zv[V], gv[V];
-        Vec<T>::load(z + off, zv);
-        if (gA != nullptr) Vec<T>::load(gA + off, gv);
+      auto one = [&](const float (&zv)[V], const float (&gv)[V]) {
 #pragma unroll
         for (int k = 0; k < V; ++k) {
           float g = (gA != nullptr ? gv[k] * gt[k] : 0.f) + dp[k];
@@ -57,6 +53,25 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(
           a1[k] += dy;
           a2[k] = fmaf(dy, (zv[k] - mu[k]) * is[k], a2[k]);
         }
+      };
+      const size_t base = (size_t)b * P * C + c0;
+      const int step = gridDim.x * ppb;
+      int p = blockIdx.x * ppb + slot;
+      for (; p + step < P; p += 2 * step) {          // two pixels per trip: four loads in flight before the math
+        const size_t o0 = base + (size_t)p * C, o1 = base + (size_t)(p + step) * C;
+        float z0[V], z1[V], g0[V], g1[V];
+        Vec<T>::load(z + o0, z0);
+        Vec<T>::load(z + o1, z1);
+        if (gA != nullptr) { Vec<T>::load(gA + o0, g0); Vec<T>::load(gA + o1, g1); }
+        one(z0, g0);
+        one(z1, g1);
+      }
+      if (p < P) {
+        const size_t o0 = base + (size_t)p * C;
+        float z0[V], g0[V];
+        Vec<T>::load(z + o0, z0);
+        if (gA != nullptr) Vec<T>::load(gA + o0, g0);
+        one(z0, g0);
       }
 #pragma unroll
       for (int k = 0; k < V; ++k) { atomicAdd(&smem[c0 + k], a1[k]); atomicAdd(&smem[C + c0 + k], a2[k]); }
@@ -82,6 +97,8 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ s1, const doub
   }
 }
 
+// pass 2: dz = scale * (dy - c1 - xhat * c2).  A thread keeps one channel vector (its BatchNorm constants live in
+// registers) and walks the pixels of one sample two at a time (both pixels' loads in flight before the math).
 template <typename T>
 __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(
     const T* __restrict__ gA, const float* __restrict__ gate, const float* __restrict__ dpool,
@@ -89,24 +106,52 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(
     T* __restrict__ dz, int B, int P, int C) {
   constexpr int V = Vec<T>::N;
   const int cv = C / V;
-  const long long nvec = (long long)B * P * cv;
-  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += (long long)gridDim.x * kThreads) {
-    const int c0 = (int)(i % cv) * V;
-    const int b = (int)(i / ((long long)P * cv));
-    float zv[V], gv[V], o[V];
-    Vec<T>::load(z + i * V, zv);
-    if (gA != nullptr) Vec<T>::load(gA + i * V, gv);
+  const int tcv = cv < kThreads ? cv : kThreads;
+  const int ppb = kThreads / tcv;
+  const int slot = threadIdx.x / tcv;
+  const int b = blockIdx.y;
+  if (slot >= ppb) return;
+  for (int cvi = threadIdx.x % tcv; cvi < cv; cvi += tcv) {
+    const int c0 = cvi * V;
+    float sc[V], sh[V], mu[V], is[V], k1[V], k2[V], gt[V], dp[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       const int c = c0 + k;
-      float g = (gA != nullptr ? gv[k] * (gate != nullptr ? gate[(size_t)b * C + c] : 1.f) : 0.f) +
-                (dpool != nullptr ? dpool[(size_t)b * C + c] : 0.f);
-      float sc = bn.scale[c];
-      float dy = g * act_bwd(fmaf(zv[k], sc, bn.shift[c]), bn.act);
-      float xhat = (zv[k] - bn.mean[c]) * bn.invstd[c];
-      o[k] = sc * (dy - c1[c] - xhat * c2[c]);
+      sc[k] = bn.scale[c]; sh[k] = bn.shift[c]; mu[k] = bn.mean[c]; is[k] = bn.invstd[c];
+      k1[k] = c1[c]; k2[k] = c2[c];
+      gt[k] = gate != nullptr ? gate[(size_t)b * C + c] : 1.f;
+      dp[k] = dpool != nullptr ? dpool[(size_t)b * C + c] : 0.f;
     }
-    Vec<T>::store(dz + i * V, o);
+    const size_t base = (size_t)b * P * C + c0;
+    const int step = gridDim.x * ppb;
+    auto one = [&](const float (&zv)[V], const float (&gv)[V], size_t off) {
+      float o[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const float g = (gA != nullptr ? gv[k] * gt[k] : 0.f) + dp[k];
+        const float dy = g * act_bwd(fmaf(zv[k], sc[k], sh[k]), bn.act);
+        const float xhat = (zv[k] - mu[k]) * is[k];
+        o[k] = sc[k] * (dy - k1[k] - xhat * k2[k]);
+      }
+      Vec<T>::store(dz + off, o);
+    };
+    int p = blockIdx.x * ppb + slot;
+    for (; p + step < P; p += 2 * step) {
+      const size_t o0 = base + (size_t)p * C, o1 = base + (size_t)(p + step) * C;
+      float z0[V], z1[V], g0[V], g1[V];
+      Vec<T>::load(z + o0, z0);
+      Vec<T>::load(z + o1, z1);
+      if (gA != nullptr) { Vec<T>::load(gA + o0, g0); Vec<T>::load(gA + o1, g1); }
+      one(z0, g0, o0);
+      one(z1, g1, o1);
+    }
+    if (p < P) {
+      const size_t o0 = base + (size_t)p * C;
+      float z0[V], g0[V];
+      Vec<T>::load(z + o0, z0);
+      if (gA != nullptr) Vec<T>::load(gA + o0, g0);
+      one(z0, g0, o0);
+    }
   }
 }
 
@@ -525,8 +570,12 @@ int eat_bn_bwd_apply(const void* gA, const float* gate, const float* dpool, cons
   BnCtx bn{scale, shift, mean, invstd, act};
   const int V = dtype == EAT_BF16 ? 8 : 4;
   if (C % V != 0) { eat_set_error("bn_bwd_apply: channels must be a multiple of the vector width"); return EAT_ERR_ARG; }
-  long long nvec = (long long)B * P * (C / V);
-  int grid = (int)min((long long)148 * 16, ceil_div_ll(nvec, kThreads));
+  const int cv = C / V, tcv = cv < kThreads ? cv : kThreads, ppb = kThreads / tcv;
+  // ~16 CTAs per SM in total, at least 2 pixels per thread
+  int gx = ceil_div(P, 2 * ppb);
+  const int cap = max(1, (148 * 16) / max(B, 1));
+  if (gx > cap) gx = cap;
+  dim3 grid(gx < 1 ? 1 : gx, B);
   if (dtype == EAT_BF16)
     bn_bwd_apply_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)gA, gate, dpool, (const __nv_bfloat16*)z, bn, c1, c2, (__nv_bfloat16*)dz, B, P, C);
   else

@@ -49,8 +49,11 @@ def test_mn_train_step_matches_reference_vectors(tag, gemm):
         ref = g["grad_norm"][i]
         idx = torch.linspace(0, gr.numel() - 1, 4).long()
         samp = gr.flatten()[idx].numpy()
+        # absolute floor 1e-7: a BatchNorm bias that feeds another training-mode BatchNorm (features.1.block.1.1.bias)
+        # has an analytically zero gradient; both implementations return fp32 summation noise of order 1e-8 there,
+        # against gradients of order 1e-3 elsewhere
         ok = abs(gn - ref) <= norm_tol * ref + 1e-7 and \
-            np.abs(samp - g["grad_samples"][i]).max() <= samp_tol * max(gr.abs().max().item(), 1e-7) + 1e-8
+            np.abs(samp - g["grad_samples"][i]).max() <= samp_tol * max(gr.abs().max().item(), 1e-7) + 1e-7
         if not ok:
             bad.append(f"{n}: norm {gn:.6e} vs {ref:.6e}; samples {samp} vs {g['grad_samples'][i]}")
     assert not bad, "\n".join(bad[:40])
