@@ -99,6 +99,10 @@ int dw_wgrad_slide_launch(const void* dz, const void* in, InXform xf, float* dw,
 int dw_dgrad2_slide_launch(const void* dz, const float* wt, long long wt_bstride, const void* res, void* din, int dtype,
                            int B, int F, int Tn, int C, int k, cudaStream_t st);
 
+// CUDA-core weight gradient for narrow 1x1 convolutions (wgrad_narrow.cu); EAT_ERR_UNSUPPORTED = shape out of range
+int wgrad_narrow_launch(const float* G, const float* A, float* dW, long long M, int N, int K, const float* in_scale,
+                        const float* in_shift, int in_act, cudaStream_t st);
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

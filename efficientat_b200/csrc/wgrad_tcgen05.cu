@@ -334,6 +334,11 @@ extern "C" int eat_pw_tc_wgrad(const void* G, int g_dtype, const void* A, int a_
   if (M >= (1ll << 31) - MB) { eat_set_error("pw_tc_wgrad: M too large"); return EAT_ERR_ARG; }
   if ((((uintptr_t)G) | ((uintptr_t)A) | ((uintptr_t)dW)) & 15) { eat_set_error("pw_tc_wgrad: operands must be 16-byte aligned"); return EAT_ERR_ARG; }
   if (K % 4 != 0) { eat_set_error("pw_tc_wgrad: K must be a multiple of 4"); return EAT_ERR_ARG; }
+  if (a_dtype == EAT_F32 && gate == nullptr) {
+    // narrowest layers (N*K <= 512, huge M): exact-fp32 CUDA-core kernel, see wgrad_narrow.cu for the measurements
+    const int rc = wgrad_narrow_launch((const float*)G, (const float*)A, dW, M, N, K, in_scale, in_shift, in_act, st);
+    if (rc != EAT_ERR_UNSUPPORTED) return rc;
+  }
   WgParams p;
   p.G = G; p.A = A; p.dW = dW; p.M = (int)M; p.N = N; p.K = K;
   p.xf = InXform{in_scale, in_shift, gate, in_act, rows_per_sample > 0 ? rows_per_sample : 1};

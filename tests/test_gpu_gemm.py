@@ -125,7 +125,11 @@ def test_tc_wgrad_matches_torch(dtype):
     st = torch.cuda.current_stream().cuda_stream
     code = 0 if dtype == torch.float32 else 1
     cases = [(4096, 64, 16, 0), (5000, 72, 24, 1), (3000, 24, 72, 2), (2048, 240, 40, 0), (1100, 112, 672, 3),
-             (1024, 960, 160, 0), (700, 160, 960, 1), (40000, 16, 16, 2), (2000, 200, 80, 0), (1500, 8, 8, 0)]
+             (1024, 960, 160, 0), (700, 160, 960, 1), (40000, 16, 16, 2), (2000, 200, 80, 0), (1500, 8, 8, 0),
+             # narrow layers with a long reduction: N*K <= 512 in fp32 storage takes the CUDA-core kernel
+             # (csrc/wgrad_narrow.cu); the wider ones stay on tensor cores
+             (70001, 16, 16, 0), (66000, 64, 16, 1), (65537, 24, 64, 1), (80000, 72, 24, 0), (70003, 24, 72, 1),
+             (66001, 8, 8, 1), (70000, 16, 16, 2), (66003, 32, 16, 1), (65540, 16, 24, 3)]
     for (M, N, K, variant) in cases:
         G = (torch.randn(M, N, device="cuda", generator=g) * 0.1).to(dtype)
         A = torch.randn(M, K, device="cuda", generator=g).to(dtype)
