@@ -476,11 +476,13 @@ __global__ void __launch_bounds__(kST, MINB) dw_wgrad_slide_kernel(const WgArgs 
 #pragma unroll
             for (int i = 0; i < V; ++i) dzw[l][p][i] = 0.f;
 
-        auto feed = [&](int irow, auto ph_tag) {
+        // an input row is loaded (raw) by ld() and later transformed + multiplied by mac(); for S = 2 the even and the
+        // odd row of a step are both requested before either is used (twice the bytes in flight per thread)
+        float ve[NIN][V], vo[S == 2 ? NIN : 1][V];
+        auto ld = [&](int irow, auto ph_tag) {
           constexpr int PH = decltype(ph_tag)::value;
-          if (irow < 0 || irow >= F) return;
+          float (&v)[NIN][V] = *reinterpret_cast<float (*)[NIN][V]>(PH == 0 ? &ve[0][0] : &vo[0][0]);
           const T* rp = colp + (long long)irow * rowstride;
-          float v[NIN][V];
 #pragma unroll
           for (int j = 0; j < NIN; ++j) {
             if ((cmask >> j) & 1u) VecW<T, V>::load(rp + (size_t)j * C, v[j]);
@@ -489,6 +491,10 @@ __global__ void __launch_bounds__(kST, MINB) dw_wgrad_slide_kernel(const WgArgs 
               for (int i = 0; i < V; ++i) v[j][i] = 0.f;
             }
           }
+        };
+        auto mac = [&](auto ph_tag) {
+          constexpr int PH = decltype(ph_tag)::value;
+          float (&v)[NIN][V] = *reinterpret_cast<float (*)[NIN][V]>(PH == 0 ? &ve[0][0] : &vo[0][0]);
           if (kXf) {
 #pragma unroll
             for (int j = 0; j < NIN; ++j) {
@@ -541,8 +547,18 @@ __global__ void __launch_bounds__(kST, MINB) dw_wgrad_slide_kernel(const WgArgs 
 #pragma unroll
               for (int i = 0; i < V; ++i) dzw[L - 1][p][i] = 0.f;
           }
-          feed(i0 + n * S, Ph0{});
-          if (S == 2 && n < nrows + (K - 3) / 2) feed(i0 + 2 * n + 1, Ph1{});   // odd kernel rows reach dz rows n .. n - (K-3)/2
+          const int ie = i0 + n * S;
+          const bool ev = ie >= 0 && ie < F;
+          if (ev) ld(ie, Ph0{});
+          if (S == 2) {
+            const int io = ie + 1;                                    // odd kernel rows reach dz rows n .. n-(K-3)/2
+            const bool od = (n < nrows + (K - 3) / 2) && io >= 0 && io < F;
+            if (od) ld(io, Ph1{});
+            if (ev) mac(Ph0{});
+            if (od) mac(Ph1{});
+          } else if (ev) {
+            mac(Ph0{});
+          }
         }
       }
     }
@@ -576,13 +592,13 @@ template <typename T, int K, int V, int P, int MINB>
 int launch_wg_slide(WgArgs a, int stride, int xact_code, cudaStream_t st) {
   const int cv = a.C / V;
   a.per_sample = a.dw_bstride != 0 ? 1 : 0;
-  const SlidePlan pl = plan_slide(a.B, a.Fo, a.To, cv, V, P, stride, K, MINB, a.per_sample != 0);
+  const SlidePlan pl = plan_slide(a.B, a.Fo, a.To, cv, V, P, stride, K, stride == 2 ? 3 : MINB, a.per_sample != 0);
   a.chunks = pl.chunks; a.cvc = pl.cvc; a.seg_rows = pl.seg_rows;
   dim3 grid(pl.chunks * pl.groups, pl.gy);
   const size_t smem = (size_t)K * K * a.cvc * V * sizeof(float);
   int rc;
   if (stride == 1) rc = launch_wg_act<T, K, 1, P, V, MINB>(a, xact_code, grid, smem, st);
-  else rc = launch_wg_act<T, K, 2, P, V, MINB>(a, xact_code, grid, smem, st);
+  else rc = launch_wg_act<T, K, 2, P, V, 3>(a, xact_code, grid, smem, st);     // two row buffers: 168 registers
   if (rc != EAT_OK) return rc;
   EAT_CHECK_LAUNCH();
   return EAT_OK;
