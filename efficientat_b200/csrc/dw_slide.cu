@@ -478,10 +478,10 @@ __global__ void __launch_bounds__(kST, MINB) dw_wgrad_slide_kernel(const WgArgs 
 
         // an input row is loaded (raw) by ld() and later transformed + multiplied by mac(); for S = 2 the even and the
         // odd row of a step are both requested before either is used (twice the bytes in flight per thread)
-        float ve[NIN][V], vo[S == 2 ? NIN : 1][V];
-        auto ld = [&](int irow, auto ph_tag) {
-          constexpr int PH = decltype(ph_tag)::value;
-          float (&v)[NIN][V] = *reinterpret_cast<float (*)[NIN][V]>(PH == 0 ? &ve[0][0] : &vo[0][0]);
+        float ve[NIN][V], vo[NIN][V];            // two row buffers: even/odd row of a stride-2 step, ping-pong for stride 1
+        auto ld = [&](int irow, auto buf_tag) {
+          constexpr int BUF = decltype(buf_tag)::value;
+          float (&v)[NIN][V] = *reinterpret_cast<float (*)[NIN][V]>(BUF == 0 ? &ve[0][0] : &vo[0][0]);
           const T* rp = colp + (long long)irow * rowstride;
 #pragma unroll
           for (int j = 0; j < NIN; ++j) {
@@ -492,9 +492,10 @@ __global__ void __launch_bounds__(kST, MINB) dw_wgrad_slide_kernel(const WgArgs 
             }
           }
         };
-        auto mac = [&](auto ph_tag) {
+        auto mac = [&](auto buf_tag, auto ph_tag) {
+          constexpr int BUF = decltype(buf_tag)::value;
           constexpr int PH = decltype(ph_tag)::value;
-          float (&v)[NIN][V] = *reinterpret_cast<float (*)[NIN][V]>(PH == 0 ? &ve[0][0] : &vo[0][0]);
+          float (&v)[NIN][V] = *reinterpret_cast<float (*)[NIN][V]>(BUF == 0 ? &ve[0][0] : &vo[0][0]);
           if (kXf) {
 #pragma unroll
             for (int j = 0; j < NIN; ++j) {
@@ -524,7 +525,7 @@ __global__ void __launch_bounds__(kST, MINB) dw_wgrad_slide_kernel(const WgArgs 
         // step n: the window slides to dz rows n-(L-1) .. n (relative to fo_a), then input row i0 + n*S (and, for
         // S = 2, i0 + 2n + 1 with the middle kernel row) meets the dz rows it was multiplied with in the forward pass
         const int steps = nrows + L - 1;
-        for (int n = 0; n < steps; ++n) {
+        auto slide_window = [&](int n) {
 #pragma unroll
           for (int l = 0; l + 1 < L; ++l)
 #pragma unroll
@@ -547,17 +548,30 @@ __global__ void __launch_bounds__(kST, MINB) dw_wgrad_slide_kernel(const WgArgs 
 #pragma unroll
               for (int i = 0; i < V; ++i) dzw[L - 1][p][i] = 0.f;
           }
-          const int ie = i0 + n * S;
-          const bool ev = ie >= 0 && ie < F;
-          if (ev) ld(ie, Ph0{});
-          if (S == 2) {
-            const int io = ie + 1;                                    // odd kernel rows reach dz rows n .. n-(K-3)/2
+        };
+        if (S == 2) {
+          for (int n = 0; n < steps; ++n) {
+            slide_window(n);
+            const int ie = i0 + 2 * n, io = ie + 1;                   // odd kernel rows reach dz rows n .. n-(K-3)/2
+            const bool ev = ie >= 0 && ie < F;
             const bool od = (n < nrows + (K - 3) / 2) && io >= 0 && io < F;
+            if (ev) ld(ie, Ph0{});
             if (od) ld(io, Ph1{});
-            if (ev) mac(Ph0{});
-            if (od) mac(Ph1{});
-          } else if (ev) {
-            mac(Ph0{});
+            if (ev) mac(Ph0{}, Ph0{});
+            if (od) mac(Ph1{}, Ph1{});
+          }
+        } else {
+          // stride 1: row n+1 is requested into the other buffer before row n is multiplied
+          auto step = [&](int n, auto cur, auto nxt) {
+            slide_window(n);
+            const int ie = i0 + n;
+            if (n + 1 < steps && ie + 1 >= 0 && ie + 1 < F) ld(ie + 1, nxt);
+            if (ie >= 0 && ie < F) mac(cur, Ph0{});
+          };
+          if (i0 >= 0 && i0 < F) ld(i0, Ph0{});
+          for (int n = 0; n < steps; n += 2) {
+            step(n, Ph0{}, Ph1{});
+            if (n + 1 < steps) step(n + 1, Ph1{}, Ph0{});
           }
         }
       }
@@ -811,7 +825,7 @@ int dw_wgrad_slide_launch(const void* dz, const void* in, InXform xf, float* dw,
   const int xact_code = xf.scale != nullptr ? xf.act : -1;
   if (dtype == EAT_BF16) return launch_wg_slide<__nv_bfloat16, 3, 8, 1, 3>(a, stride, xact_code, st);
   if (k == 5) return launch_wg_slide<float, 5, 2, 4, 3>(a, stride, xact_code, st);
-  return launch_wg_slide<float, 3, 4, 4, 4>(a, stride, xact_code, st);
+  return launch_wg_slide<float, 3, 4, 4, 3>(a, stride, xact_code, st);
 }
 
 int dw_dgrad2_slide_launch(const void* dz, const float* wt, long long wt_bstride, const void* res, void* din, int dtype,
