@@ -182,8 +182,11 @@ def algo_bytes(name, a):
 # DRAM traffic of the dominant kernel from one `ncu --set full` capture (profiles/README.md): dram read + write bytes
 # relative to the algorithmic bytes of the captured launch.  Used to scale the per-launch `traffic` figure.
 NCU_TRAFFIC = {
-    "eat_pw_tc_fwd": {"dram_bytes": 65.619712e6 + 202.606080e6, "algorithmic_bytes": 1024000 * (16 + 64) * 4 + 64 * 16 * 4,
-                      "capture": "profiles/r01_ncu_pw_tc_fwd_K16_N64_M1M_fp32_eval.csv"},
+    # `ncu --set full` capture of the training-forward launch M = 2 048 000, K = 16, N = 64 (ID 11 in the csv):
+    # dram__bytes_read 131.4 MB + dram__bytes_write 465.5 MB against 655.4 MB algorithmic (the tail of the output is
+    # still dirty in the 126 MB L2 when the kernel ends: no re-reads)
+    "eat_pw_tc_fwd": {"dram_bytes": 131.385e6 + 465.466112e6, "algorithmic_bytes": 2048000 * (16 + 64) * 4 + 64 * 16 * 4,
+                      "capture": "profiles/r01_ncu_full_final_kernels.csv"},
 }
 
 
@@ -370,9 +373,9 @@ def run_ours(args):
         achieved = (top_bytes / 1e9) / (top_ms * 1e-3) if (bytes_ok and top_ms > 0) else None
         shares = {k: round(v[0] / sum(x[0] for x in prof.values()), 4) for k, v in
                   sorted(prof.items(), key=lambda kv: -kv[1][0])[:8]}
-        if os.environ.get("EAT_BENCH_KERNELS"):      # full per-entry-point table (ms per step, launches per step) on stderr
+        if os.environ.get("EAT_BENCH_KERNELS"):      # full per-entry-point table of the instrumented eager step, on stderr
             for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0]):
-                print(f"  {k:28s} {v[0] / args.steps:8.3f} ms/step {v[1] // args.steps:5d} launches"
+                print(f"  {k:28s} {v[0]:8.3f} ms/step {v[1]:5d} launches"
                       + (f" {v[2] / 1e6 / v[0]:8.0f} GB/s" if v[3] and v[0] > 0 else ""), file=sys.stderr)
         line = {
             "metric": METRIC if (args.mode == "train" and args.model == "mn10") else
