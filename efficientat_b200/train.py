@@ -19,6 +19,46 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+class HostPrefetcher:
+    """Double-buffered host -> device feed for the training loop (the role of the reference's pinned-memory DataLoader,
+    ex_audioset.py:104-110): batch i+1 is copied from pinned host memory on a side stream while step i runs.
+
+        pf = HostPrefetcher(device)
+        pf.submit(0, first_batch)
+        for i, nxt in enumerate(batches[1:] + [None]):
+            if nxt is not None: pf.submit((i + 1) % 2, nxt)
+            wave, y, teacher = pf.get(i % 2)
+            loss = trainer.step(wave, y, teacher)
+            pf.release(i % 2)
+    """
+
+    def __init__(self, device, slots=2):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self.bufs = [None] * slots
+        self.ready = [torch.cuda.Event() for _ in range(slots)]
+        self.free = [torch.cuda.Event() for _ in range(slots)]
+        for e in self.free:
+            e.record(torch.cuda.current_stream(self.device))
+
+    def submit(self, slot, host_tensors):
+        """enqueue the copy of one batch (a tuple of pinned CPU tensors) into slot `slot`"""
+        if self.bufs[slot] is None or any(b.shape != h.shape or b.dtype != h.dtype for b, h in zip(self.bufs[slot], host_tensors)):
+            self.bufs[slot] = tuple(torch.empty(h.shape, dtype=h.dtype, device=self.device) for h in host_tensors)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self.free[slot])          # the step that read this slot two batches ago is done
+            for b, h in zip(self.bufs[slot], host_tensors):
+                b.copy_(h, non_blocking=True)
+            self.ready[slot].record(self.stream)
+
+    def get(self, slot):
+        torch.cuda.current_stream(self.device).wait_event(self.ready[slot])
+        return self.bufs[slot]
+
+    def release(self, slot):
+        self.free[slot].record(torch.cuda.current_stream(self.device))
+
+
 class AudioSetTrainer:
     def __init__(self, model, mel, lr=8e-4, kd_lambda=0.1, mixup_alpha=0.3, weight_decay=0.0, adamw=False,
                  betas=(0.9, 0.999), eps=1e-8, process_group=None, cuda_graph=False):
