@@ -5,8 +5,6 @@
 //   apply  : dz = gamma*invstd * (dy - s1/M - xhat * s2/M)
 // where the upstream gradient may be composed on the fly, g = gA * gate[b,c] + dpool[b,c]
 // (squeeze-excitation gate and the gradient of a spatial mean), so those products are never stored.
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace {
@@ -230,62 +228,9 @@ __global__ void __launch_bounds__(kThreads) se_fc_bwd_kernel(const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------
-// Depthwise conv backward.  dgrad: gather over output pixels that read this input pixel.
-template <typename T, int K, int S>
-__global__ void __launch_bounds__(kThreads) dw_dgrad_kernel(const T* __restrict__ dz, const float* __restrict__ wt,
-                                                            const T* __restrict__ res, T* __restrict__ din,
-                                                            int F, int Tn, int Fo, int To, int C, long long wt_bstride) {
-  constexpr int V = Vec<T>::N;
-  constexpr int PAD = (K - 1) / 2;
-  const int cv = C / V;
-  const int b = blockIdx.y;
-  wt += (size_t)b * wt_bstride;
-  const long long nvec = (long long)F * Tn * cv;
-  const T* dzb = dz + (size_t)b * Fo * To * C;
-  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += (long long)gridDim.x * kThreads) {
-    const int c0 = (int)(i % cv) * V;
-    const int t = (int)((i / cv) % Tn);
-    const int f = (int)(i / ((long long)cv * Tn));
-    float acc[V];
-#pragma unroll
-    for (int k = 0; k < V; ++k) acc[k] = 0.f;
-#pragma unroll
-    for (int ky = 0; ky < K; ++ky) {
-      const int nf = f + PAD - ky;
-      if (nf < 0 || nf % S != 0) continue;
-      const int fo = nf / S;
-      if (fo >= Fo) continue;
-#pragma unroll
-      for (int kx = 0; kx < K; ++kx) {
-        const int nt = t + PAD - kx;
-        if (nt < 0 || nt % S != 0) continue;
-        const int to = nt / S;
-        if (to >= To) continue;
-        float g[V];
-        Vec<T>::load(dzb + ((size_t)fo * To + to) * C + c0, g);
-        const float4* wp = reinterpret_cast<const float4*>(wt + (size_t)(ky * K + kx) * C + c0);
-#pragma unroll
-        for (int q = 0; q < V / 4; ++q) {
-          float4 w4 = __ldg(wp + q);
-          acc[4 * q] = fmaf(g[4 * q], w4.x, acc[4 * q]);
-          acc[4 * q + 1] = fmaf(g[4 * q + 1], w4.y, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(g[4 * q + 2], w4.z, acc[4 * q + 2]);
-          acc[4 * q + 3] = fmaf(g[4 * q + 3], w4.w, acc[4 * q + 3]);
-        }
-      }
-    }
-    const size_t off = (size_t)b * F * Tn * C + (size_t)i * V;
-    if (res != nullptr) {
-      float r[V];
-      Vec<T>::load(res + off, r);
-#pragma unroll
-      for (int k = 0; k < V; ++k) acc[k] += r[k];
-    }
-    Vec<T>::store(din + off, acc);
-  }
-}
-
-// Shared-memory tiled depthwise weight gradient (same contract as dw_wgrad_kernel).  A CTA stages the transformed
+// Depthwise conv backward.  The data gradients and the fp32 weight gradients live in dw_slide.cu / conv_kernels.cu;
+// the kernel below is the weight gradient of the remaining case (bf16 storage, 5x5).
+// Shared-memory tiled depthwise weight gradient: dw[c, ky, kx] += sum dz * xf(in).  A CTA stages the transformed
 // input tile and the dz tile of one sample / 32-channel chunk in shared memory (BatchNorm+activation applied once
 // per input element), keeps all K*K tap accumulators of its channel slice in registers across its tiles, and
 // reduces them once at the end (shared atomics, then one global atomic per tap and channel).
@@ -509,14 +454,8 @@ int launch_dw_bwd(int which, const void* dz, const float* wt, const void* in, In
   const int Fo = (F + 2 * pad - k) / stride + 1, To = (Tn + 2 * pad - k) / stride + 1;
   const int cv = C / V;
   if (which == 0) {
-    long long nvec = (long long)F * Tn * cv;
-    int gx = (int)min((long long)max(1, (148 * 16) / max(B, 1)), ceil_div_ll(nvec, kThreads));
-    dim3 grid(gx < 1 ? 1 : gx, B);
-#define EAT_DG(KK, SS) dw_dgrad_kernel<T, KK, SS><<<grid, kThreads, 0, st>>>((const T*)dz, wt, (const T*)res, (T*)din, F, Tn, Fo, To, C, wt_bstride)
-    if (k == 3 && stride == 1) EAT_DG(3, 1); else if (k == 3 && stride == 2) EAT_DG(3, 2);
-    else if (k == 5 && stride == 1) EAT_DG(5, 1); else if (k == 5 && stride == 2) EAT_DG(5, 2);
-    else { eat_set_error("dw dgrad: only k in {3,5}, stride in {1,2}"); return EAT_ERR_UNSUPPORTED; }
-#undef EAT_DG
+    eat_set_error("dw dgrad: unsupported kernel size / stride");
+    return EAT_ERR_UNSUPPORTED;
   } else {
     const int FR = stride == 1 ? 8 : 4, TT = stride == 1 ? 32 : 16;
     const int IR = (FR - 1) * stride + k, IT = (TT - 1) * stride + k;
@@ -614,8 +553,7 @@ int eat_dw_conv_dgrad(const void* dz, const float* wt, long long wt_bstride, con
                       int F, int T, int C, int k, int stride, cudaStream_t st) {
   if (B == 0) return EAT_OK;
   if (stride == 1 && (k == 3 || k == 5)) return eat_dw_conv_dgrad_s1(dz, wt, wt_bstride, res, din, dtype, B, F, T, C, k, st);
-  static const int impl = [] { const char* e = getenv("EAT_DW_IMPL"); return (e && e[0] == 'o') ? 0 : 1; }();   // dev switch: "old"
-  if (impl == 1 && stride == 2 && (k == 3 || k == 5)) return dw_dgrad2_slide_launch(dz, wt, wt_bstride, res, din, dtype, B, F, T, C, k, st);
+  if (stride == 2 && (k == 3 || k == 5)) return dw_dgrad2_slide_launch(dz, wt, wt_bstride, res, din, dtype, B, F, T, C, k, st);
   InXform xf{nullptr, nullptr, nullptr, 0, 0};
   if (dtype == EAT_BF16) return launch_dw_bwd<__nv_bfloat16>(0, dz, wt, nullptr, xf, res, din, nullptr, B, F, T, C, k, stride, st, wt_bstride);
   return launch_dw_bwd<float>(0, dz, wt, nullptr, xf, res, din, nullptr, B, F, T, C, k, stride, st, wt_bstride);
@@ -626,8 +564,7 @@ int eat_dw_conv_wgrad(const void* dz, const void* in, const float* in_scale, con
                       cudaStream_t st) {
   if (B == 0) return EAT_OK;
   InXform xf{in_scale, in_shift, nullptr, in_act, 0};
-  static const int impl = [] { const char* e = getenv("EAT_DW_IMPL"); return (e && e[0] == 'o') ? 0 : 1; }();   // dev switch: "old"
-  if (impl == 1 && (k == 3 || (k == 5 && dtype != EAT_BF16)) && (stride == 1 || stride == 2))
+  if ((k == 3 || (k == 5 && dtype != EAT_BF16)) && (stride == 1 || stride == 2))
     return dw_wgrad_slide_launch(dz, in, xf, dw, dw_bstride, dtype, B, F, T, C, k, stride, st);
   if (dtype == EAT_BF16) return launch_dw_bwd<__nv_bfloat16>(1, dz, nullptr, in, xf, nullptr, nullptr, dw, B, F, T, C, k, stride, st, 0, dw_bstride);
   return launch_dw_bwd<float>(1, dz, nullptr, in, xf, nullptr, nullptr, dw, B, F, T, C, k, stride, st, 0, dw_bstride);

@@ -6,8 +6,6 @@
 // statistics (training).  Reference semantics: torchvision ConvNormActivation as used at
 // models/mn/model.py:125-133 and models/mn/block_types.py:140-170; SqueezeExcitation
 // models/mn/block_types.py:72-83.
-#include <cstdlib>
-
 #include "common.cuh"
 #include <stdlib.h>
 
@@ -117,171 +115,17 @@ __global__ void __launch_bounds__(kThreads) stem_kernel(
 
 // ------------------------------------------------------------------------------------------
 // Depthwise k x k conv, pad (k-1)/2, stride S.  in [B, F, T, C] -> out [B, Fo, To, C].
-// wt: repacked weights [k*k][C] (flip != 0 reads them mirrored: the stride-1 data gradient is the same
-// convolution with the kernel flipped).  Each thread: one channel vector, a strip of P output columns whose
-// input span ((P-1)*S + K vectors per kernel row) is loaded/transformed once and reused by all taps.
-// grid = (chunks, B) so per-(sample, channel) pooling stays inside a CTA column.
-// DyMN extras for the depthwise kernel (reference models/dymn/dy_block.py): per-sample mixed weights
-// (DynamicConv :111-127), DyReLU-B (:172-188) and coordinate attention (:195-201) as a register-resident epilogue.
-
+// wt: repacked weights [k*k][C] (flip != 0 reads them mirrored: the stride-1 data gradient is the same convolution
+// with the kernel flipped).  grid = (chunks x tile groups, B): per-(sample, channel) pooling stays inside a CTA column.
+// All 3x3 cases and the 5x5 training forward run in the register sliding-window kernel (dw_slide.cu); the kernel below
+// serves the 5x5 eval (squeeze-excitation pooling / DyMN epilogue) and 5x5 stride-1 data-gradient cases, where it
+// measured faster (profiles/README.md).
 // MODE 0: training forward (optional input BN+act, raw output + batch statistics)
 // MODE 1: eval forward (folded BN + act epilogue, SE pooling, DyMN epilogue)     MODE 2: stride-1 data gradient
-template <typename T, int K, int S, int P, int MINB, int MODE>
-__global__ void __launch_bounds__(kThreads, MINB) dw_kernel(
-    const T* __restrict__ in, const float* __restrict__ wt, T* __restrict__ out,
-    int F, int Tn, int Fo, int To, int C, InXform xf,
-    const float* __restrict__ scale, const float* __restrict__ shift, int act, const T* __restrict__ res, int flip,
-    float* __restrict__ pool /*[B,C] or null*/, double* __restrict__ stat_sum, double* __restrict__ stat_sq, DyEpi dy) {
-  constexpr int V = Vec<T>::N;
-  constexpr bool kAff = MODE == 1, kStats = MODE == 0, kXf = MODE == 0, kRes = MODE == 2, kDy = MODE == 1, kPool = MODE == 1;
-  constexpr int NIN = (P - 1) * S + K;
-  constexpr int PAD = (K - 1) / 2;
-  extern __shared__ float smem[];
-  float* s_sum = smem;       // [C]
-  float* s_sq = smem + C;    // [C]
-  const bool need_red = (kPool && pool != nullptr) || (kStats && stat_sum != nullptr);
-  if (need_red) {
-    for (int i = threadIdx.x; i < 2 * C; i += kThreads) s_sum[i] = 0.f;
-    __syncthreads();
-  }
-  const int cv = C / V;
-  const int ppb = kThreads / cv > 0 ? kThreads / cv : 1;
-  const int b = blockIdx.y;
-  const int strips = ceil_div(To, P);
-  const int units = Fo * strips;
-  float lsum[V], lsq[V];
-#pragma unroll
-  for (int i = 0; i < V; ++i) { lsum[i] = 0.f; lsq[i] = 0.f; }
-  const T* inb = in + (size_t)b * F * Tn * C;
-  T* outb = out + (size_t)b * Fo * To * C;
-  const T* resb = (kRes && res != nullptr) ? res + (size_t)b * Fo * To * C : nullptr;
-  wt += (size_t)b * dy.wt_bstride;
-  // channel vectors beyond kThreads are covered by looping cvi
-  for (int cvi = threadIdx.x % (cv < kThreads ? cv : kThreads); cvi < cv; cvi += kThreads) {
-    const int slot = cv < kThreads ? threadIdx.x / cv : 0;
-    if (slot >= ppb) break;
-    const int c0 = cvi * V;
-    float isc[V], ish[V];
-    if (kXf && xf.scale != nullptr) {
-#pragma unroll
-      for (int i = 0; i < V; ++i) { isc[i] = xf.scale[c0 + i]; ish[i] = xf.shift[c0 + i]; }
-    }
-    float da1[V], da2[V], db1[V], db2[V];
-    if (kDy && dy.theta != nullptr) {
-      const float* th = dy.theta + ((size_t)b * C + c0) * 4;
-#pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const float4 t4 = __ldg(reinterpret_cast<const float4*>(th) + i);
-        da1[i] = (2.f * t4.x - 1.f) * dy.lam[0] + dy.init[0];
-        da2[i] = (2.f * t4.y - 1.f) * dy.lam[1] + dy.init[1];
-        db1[i] = (2.f * t4.z - 1.f) * dy.lam[2] + dy.init[2];
-        db2[i] = (2.f * t4.w - 1.f) * dy.lam[3] + dy.init[3];
-      }
-    }
-    for (int u = blockIdx.x * ppb + slot; u < units; u += gridDim.x * ppb) {
-      const int fo = u / strips;
-      const int to0 = (u - fo * strips) * P;
-      float acc[P][V];
-#pragma unroll
-      for (int p = 0; p < P; ++p)
-#pragma unroll
-        for (int i = 0; i < V; ++i) acc[p][i] = 0.f;
-#pragma unroll
-      for (int ky = 0; ky < K; ++ky) {
-        const int f = fo * S - PAD + ky;
-        if (f < 0 || f >= F) continue;
-        const T* rowp = inb + (size_t)f * Tn * C + c0;
-        float wreg[K][V];
-#pragma unroll
-        for (int kx = 0; kx < K; ++kx) {
-          const int tap = flip ? (K * K - 1 - (ky * K + kx)) : (ky * K + kx);
-          float4 const* wp = reinterpret_cast<float4 const*>(wt + (size_t)tap * C + c0);
-#pragma unroll
-          for (int q = 0; q < V / 4; ++q) {
-            float4 t4 = __ldg(wp + q);
-            wreg[kx][4 * q] = t4.x; wreg[kx][4 * q + 1] = t4.y; wreg[kx][4 * q + 2] = t4.z; wreg[kx][4 * q + 3] = t4.w;
-          }
-        }
-#pragma unroll
-        for (int ix = 0; ix < NIN; ++ix) {
-          const int t = to0 * S - PAD + ix;
-          if (t < 0 || t >= Tn) continue;
-          float v[V];
-          Vec<T>::load(rowp + (size_t)t * C, v);
-          if (kXf && xf.scale != nullptr) {
-#pragma unroll
-            for (int i = 0; i < V; ++i) v[i] = act_fwd(fmaf(v[i], isc[i], ish[i]), xf.act);
-          }
-#pragma unroll
-          for (int p = 0; p < P; ++p) {
-            const int kx = ix - p * S;
-            if (kx >= 0 && kx < K) {
-#pragma unroll
-              for (int i = 0; i < V; ++i) acc[p][i] = fmaf(v[i], wreg[kx][i], acc[p][i]);
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int p = 0; p < P; ++p) {
-        const int to = to0 + p;
-        if (to >= To) break;
-        float o[V];
-        if (kAff && scale != nullptr) {
-#pragma unroll
-          for (int i = 0; i < V; ++i) { o[i] = act_fwd(fmaf(acc[p][i], scale[c0 + i], shift[c0 + i]), act); lsum[i] += o[i]; }
-        } else {
-#pragma unroll
-          for (int i = 0; i < V; ++i) {
-            o[i] = acc[p][i];
-            if (kStats) { lsum[i] += o[i]; lsq[i] = fmaf(o[i], o[i], lsq[i]); }
-          }
-        }
-        if (kDy && dy.theta != nullptr) {
-#pragma unroll
-          for (int i = 0; i < V; ++i) o[i] = fmaxf(fmaf(o[i], da1[i], db1[i]), fmaf(o[i], da2[i], db2[i]));
-        }
-        if (kDy && dy.ca_f != nullptr) {
-          const float* cf = dy.ca_f + ((size_t)b * Fo + fo) * C + c0;
-          const float* ct = dy.ca_t + ((size_t)b * To + to) * C + c0;
-#pragma unroll
-          for (int q = 0; q < V / 4; ++q) {
-            const float4 f4 = __ldg(reinterpret_cast<const float4*>(cf) + q), t4 = __ldg(reinterpret_cast<const float4*>(ct) + q);
-            o[4 * q] *= f4.x * t4.x; o[4 * q + 1] *= f4.y * t4.y; o[4 * q + 2] *= f4.z * t4.z; o[4 * q + 3] *= f4.w * t4.w;
-          }
-        }
-        const size_t off = ((size_t)fo * To + to) * C + c0;
-        if (resb != nullptr) {
-          float r[V];
-          Vec<T>::load(resb + off, r);
-#pragma unroll
-          for (int i = 0; i < V; ++i) o[i] += r[i];
-        }
-        Vec<T>::store(outb + off, o);
-      }
-    }
-    if (need_red) {
-#pragma unroll
-      for (int i = 0; i < V; ++i) { atomicAdd(&s_sum[c0 + i], lsum[i]); lsum[i] = 0.f; }
-      if (kStats && stat_sum != nullptr) {
-#pragma unroll
-        for (int i = 0; i < V; ++i) { atomicAdd(&s_sq[c0 + i], lsq[i]); lsq[i] = 0.f; }
-      }
-    }
-  }
-  if (need_red) {
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += kThreads) {
-      if (kPool && pool != nullptr) atomicAdd(pool + (size_t)b * C + c, s_sum[c]);
-      if (kStats && stat_sum != nullptr) { atomicAdd(stat_sum + c, (double)s_sum[c]); atomicAdd(stat_sq + c, (double)s_sq[c]); }
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------
-// Shared-memory tiled depthwise convolution (same contract as dw_kernel).  A CTA stages an input tile
+// Shared-memory tiled depthwise convolution.  A CTA stages an input tile
 // ((FR-1)*S+K rows x (TT-1)*S+K columns x 32 channels) in shared memory as fp32, applying the producing layer's
-// BatchNorm + activation ONCE per element (the register-strip kernel re-applies it for every kernel row), then
+// BatchNorm + activation ONCE per element, then
 // every thread computes a strip of P outputs for one 4-channel vector from shared memory (LDS.128).
 template <typename T, int K, int S, int MODE>
 __global__ void __launch_bounds__(kThreads, 3) dw_tile_kernel(
@@ -635,40 +479,13 @@ int launch_dw(const T* in, const float* wt, T* out, int B, int F, int Tn, int C,
   if (C % V != 0) { eat_set_error("dw conv: channels must be a multiple of the vector width"); return EAT_ERR_ARG; }
   const int pad = (k - 1) / 2;
   const int Fo = (F + 2 * pad - k) / stride + 1, To = (Tn + 2 * pad - k) / stride + 1;
-  static const int impl = [] { const char* e = getenv("EAT_DW_IMPL"); return (e && e[0] == 'o') ? 0 : 1; }();   // dev switch: "old"
   const int mode_ = (scale != nullptr || pool != nullptr || dy.theta != nullptr || dy.ca_f != nullptr) ? 1 : ((flip || res != nullptr) ? 2 : 0);
   // sliding-window kernel (dw_slide.cu) for every 3x3 case and the 5x5 training forward; the 5x5 eval / data-gradient
   // cases stay on the shared-memory tile kernel below (measured faster there: profiles/README.md)
-  if (impl == 1 && (stride == 1 || stride == 2) && (k == 3 || (k == 5 && mode_ == 0)) && !(mode_ == 2 && stride != 1))
+  if ((stride == 1 || stride == 2) && (k == 3 || (k == 5 && mode_ == 0)) && !(mode_ == 2 && stride != 1))
     return dw_slide_launch(in, wt, out, V == 8 ? EAT_BF16 : EAT_F32, B, F, Tn, C, k, stride, xf, scale, shift, act, res, flip,
                            pool, ssum, ssq, st, dy);
-  if (k == 3 || k == 5) {
-    const bool tiled = (k == 5);     // measured (profiles/r01_dw_microbench*): smem tiling pays for 5x5, not for 3x3
-    if (!tiled) {
-      const int cv = C / V;
-      const int ppb = kThreads / cv > 0 ? kThreads / cv : 1;
-      const int P = 4;      // 4-wide strips at 4 CTAs/SM measured best among {4,8} x {2,3,4} (profiles/README.md)
-      const int units = Fo * ceil_div(To, P);
-      int gx = ceil_div(units, ppb);
-      const int cap = max(1, (148 * 16) / max(B, 1));
-      if (gx > cap) gx = cap;
-      dim3 grid(gx, B);
-      size_t smem = 2 * (size_t)C * sizeof(float);
-      const int mode = (scale != nullptr || pool != nullptr || dy.theta != nullptr || dy.ca_f != nullptr) ? 1 : ((flip || res != nullptr) ? 2 : 0);
-#define EAT_DWS(SS, PP, MB)                                                                                         \
-  do {                                                                                                              \
-    if (mode == 0) dw_kernel<T, 3, SS, PP, MB, 0><<<grid, kThreads, smem, st>>>(in, wt, out, F, Tn, Fo, To, C, xf, scale, shift, act, res, flip, pool, ssum, ssq, dy); \
-    else if (mode == 1) dw_kernel<T, 3, SS, PP, MB, 1><<<grid, kThreads, smem, st>>>(in, wt, out, F, Tn, Fo, To, C, xf, scale, shift, act, res, flip, pool, ssum, ssq, dy); \
-    else dw_kernel<T, 3, SS, PP, MB, 2><<<grid, kThreads, smem, st>>>(in, wt, out, F, Tn, Fo, To, C, xf, scale, shift, act, res, flip, pool, ssum, ssq, dy); \
-  } while (0)
-      if (stride == 1) EAT_DWS(1, 4, 4);
-      else if (stride == 2) EAT_DWS(2, 4, 4);
-      else { eat_set_error("dw conv: stride must be 1 or 2"); return EAT_ERR_UNSUPPORTED; }
-#undef EAT_DWS
-      EAT_CHECK_LAUNCH();
-      return EAT_OK;
-    }
-  }
+  if (k != 5) { eat_set_error("dw conv: only k in {3,5}, stride in {1,2}"); return EAT_ERR_UNSUPPORTED; }
   // shared-memory tiled kernel: grid.x = channel chunks x tile groups (each CTA strides over its group's tiles)
   const int FR = stride == 1 ? 8 : 4, TT = stride == 1 ? 32 : 16;
   const int IR = (FR - 1) * stride + k, IT = (TT - 1) * stride + k;

@@ -115,3 +115,25 @@ def test_trainer_cuda_graph_matches_eager_steps():
     for (n, p), (_, q) in zip(m_e.named_buffers(), m_g.named_buffers()):
         assert torch.allclose(p.float(), q.float(), rtol=1e-4, atol=1e-6), n
     assert int(dict(m_g.named_buffers())["features.0.1.num_batches_tracked"]) == 4     # 3 steps + the last call
+
+
+def test_host_prefetcher_feeds_the_trainer_in_order():
+    """HostPrefetcher: batches copied on the side stream arrive intact and in order, a slot is not overwritten before
+    the step that read it has been released, and the trainer consumes the prefetched tensors directly."""
+    from efficientat_b200.train import HostPrefetcher
+    dev = torch.device("cuda", 0)
+    pf = HostPrefetcher(dev)
+    batches = [(torch.full((4, 1000), float(i)).pin_memory(), torch.full((4, 8), float(-i)).pin_memory()) for i in range(5)]
+    seen = []
+    pf.submit(0, batches[0])
+    for i in range(len(batches)):
+        if i + 1 < len(batches):
+            pf.submit((i + 1) % 2, batches[i + 1])
+        a, b = pf.get(i % 2)
+        torch.cuda._sleep(2_000_000)                 # the "step": keeps the compute stream busy while the next copy lands
+        seen.append((a.min(), a.max(), b.min(), b.max()))     # every element of batch i is i / -i
+        pf.release(i % 2)
+    torch.cuda.synchronize()
+    for i, vals in enumerate(seen):
+        got = [v.item() for v in vals]
+        assert got == [float(i), float(i), float(-i), float(-i)], (i, got)
