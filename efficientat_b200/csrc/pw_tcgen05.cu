@@ -24,6 +24,30 @@
 
 #include "tc_common.cuh"
 
+// Optional per-role cycle accounting (scripts/timing/: built with -DEAT_TC_TIMING into a separate library, never part
+// of libeat_b200.so).  Each role accumulates clock64() deltas between the marks below; one designated thread per role
+// and CTA dumps {4 accumulators, tiles} to the buffer registered with eat_debug_tc_timing().
+#ifdef EAT_TC_TIMING
+__device__ long long* g_tc_timing = nullptr;
+extern "C" int eat_debug_tc_timing(long long* buf) {
+  return cudaMemcpyToSymbol(g_tc_timing, &buf, sizeof(buf)) == cudaSuccess ? 0 : 2;
+}
+#define TC_T_DECL long long t_acc[4] = {0, 0, 0, 0}; long long t_prev = clock64(); int t_cnt = 0;
+#define TC_T_MARK(i) { const long long t_now = clock64(); t_acc[i] += t_now - t_prev; t_prev = t_now; }
+#define TC_T_COUNT ++t_cnt;
+#define TC_T_DUMP(role, cond)                                                          \
+  if ((cond) && g_tc_timing != nullptr) {                                              \
+    long long* d__ = g_tc_timing + ((size_t)blockIdx.x * 4 + (role)) * 8;              \
+    for (int i__ = 0; i__ < 4; ++i__) d__[i__] = t_acc[i__];                           \
+    d__[4] = t_cnt;                                                                    \
+  }
+#else
+#define TC_T_DECL
+#define TC_T_MARK(i)
+#define TC_T_COUNT
+#define TC_T_DUMP(role, cond)
+#endif
+
 namespace {
 
 constexpr int BM = 128;
@@ -189,6 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
     // group skips the tiles it stages nothing for before doing any of it.
     int nt = blockIdx.x / p.m_tiles, mt = blockIdx.x - nt * p.m_tiles;
     int nt2 = nt, mt2 = mt;
+    TC_T_DECL
     auto advance = [&](int& n, int& m) { m += gridDim.x; while (m >= p.m_tiles) { m -= p.m_tiles; ++n; } };
     advance(nt2, mt2);
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -232,7 +257,9 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
         if ((it & 1) != grp) continue;
         const int stage = it % STAGES;
         const uint32_t phase = (uint32_t)(it / STAGES) & 1u;
+        TC_T_MARK(0)                                     // tile walk / set-up (incl. the other group's tiles)
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        TC_T_MARK(1)                                     // wait for the stage to drain
         unsigned char* sA_hi = stage_base + stage * STAGE_BYTES;
         unsigned char* sA_lo = sA_hi + A_TILE_BYTES;                       // only used when NP == 2
         unsigned char* sB_hi = sA_hi + NP * A_TILE_BYTES;
@@ -324,11 +351,15 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
             if (r < BN && kact) store_chunk<NP>(sB_hi, sB_lo, swz(r, kc), wv[i]);
           }
         }
+        TC_T_MARK(2)                                     // loads + conversion + smem stores (A and, when not resident, B)
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+        TC_T_MARK(3)                                     // proxy fence + arrive
+        TC_T_COUNT
       }
     }
+    TC_T_DUMP(grp, gtid == 0)
   } else if (warp == kMmaWarp) {
     // ================================================================= MMA issuer (one thread)
     if (lane == 0) {
@@ -336,14 +367,18 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
       int it = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      TC_T_DECL
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        TC_T_MARK(0)                                     // loop overhead
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        TC_T_MARK(1)                                     // wait for a free TMEM accumulator (epilogue)
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN_MAX;
         for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
           const int stage = it % STAGES;
           const uint32_t phase = (uint32_t)(it / STAGES) & 1u;
           mbar_wait(bar_full + 8 * stage, phase);
+          TC_T_MARK(2)                                   // wait for a filled smem stage (producers)
           tc_fence_after();
           const uint32_t sA_hi = smem_u32(stage_base + stage * STAGE_BYTES);
           const uint32_t sA_lo = sA_hi + A_TILE_BYTES;
@@ -363,8 +398,11 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
           tc_commit(bar_empty + 8 * stage);                       // frees the smem stage when these MMAs retire
         }
         tc_commit(bar_tfull + 8 * acc);                           // accumulator complete -> epilogue
+        TC_T_MARK(3)                                     // descriptor math + MMA issue + commits
+        TC_T_COUNT
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      TC_T_DUMP(2, true)
     }
     __syncwarp();
   } else {
@@ -384,7 +422,9 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
     uint32_t acc_phase = 0;
     const bool do_stats = p.stat_sum != nullptr;
     int ent = blockIdx.x / p.m_tiles, emt = blockIdx.x - ent * p.m_tiles;
+    TC_T_DECL
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      TC_T_MARK(0)                                       // loop overhead (+ N-tile change)
       const int nt = ent, mt = emt;
       emt += gridDim.x;
       while (emt >= p.m_tiles) { emt -= p.m_tiles; ++ent; }
@@ -423,6 +463,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
         }
       }
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      TC_T_MARK(1)                                       // wait for the accumulator (MMA)
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN_MAX;
       const long long mrow0 = m0 + q * 32;
@@ -496,11 +537,15 @@ __global__ void __launch_bounds__(kThreads, 1) pw_tc_kernel(TcParams p) {
         }
         __syncwarp();
       }
+      TC_T_MARK(2)                                       // TMEM loads, transpose, epilogue math, global stores
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      TC_T_MARK(3)                                       // fence + arrive
+      TC_T_COUNT
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    TC_T_DUMP(3, ew == 0 && lane == 0)
     // final statistics flush
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (do_stats && cur_nt >= 0) {
