@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-1 final data collection (1 GPU): tests, headline bench (+cpu baseline), reference arm, variants, ncu evidence
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out/final; mkdir -p $O
 timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -3 | tee $O/pytest_gpu.txt
 timeout 900 python bench.py --steps 10 --warmup 3 2>$O/bench_default.err | tail -1 > $O/bench_fp32_b256.json; cut -c1-400 $O/bench_fp32_b256.json

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out/final; mkdir -p $O
 nvidia-smi --query-gpu=name --format=csv,noheader | head -2
 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 > $O/bench_fp32_b256_1gpu_samebox.json; cut -c1-200 $O/bench_fp32_b256_1gpu_samebox.json

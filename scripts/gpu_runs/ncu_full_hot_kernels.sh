@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 ncu --set full --import-source on --clock-control none -k regex:"dw_|pw_tc|wgrad_tc|bn_bwd" -o gpurun_out/prof_r25 -f python scripts/prof_kernels.py > gpurun_out/ncu25.log 2>&1
 tail -3 gpurun_out/ncu25.log
