@@ -842,3 +842,36 @@ int dw_dgrad2_slide_launch(const void* dz, const float* wt, long long wt_bstride
   if (dtype == EAT_BF16) return launch_dg2_slide<__nv_bfloat16>(a, k, st);
   return launch_dg2_slide<float>(a, k, st);
 }
+
+extern "C" int eat_dw_plan(int kind, int dtype, int B, int F, int T, int C, int k, int stride, int per_sample, int* plan) {
+  const int V0 = dtype == EAT_BF16 ? 8 : 4;
+  if (plan == nullptr || B < 1 || F < 1 || T < 1 || C % V0 != 0 || (k != 3 && k != 5) || (stride != 1 && stride != 2)) {
+    eat_set_error("dw_plan: invalid arguments");
+    return EAT_ERR_ARG;
+  }
+  const bool f32 = dtype != EAT_BF16;
+  const int pad = (k - 1) / 2;
+  const int Fo = (F + 2 * pad - k) / stride + 1, To = (T + 2 * pad - k) / stride + 1;
+  int V = V0, P, minb, rows, cols, S = stride, Kp = k;
+  if (kind == 0) {                                   // launch_slide
+    P = (k == 3 && stride == 1) ? (f32 ? 4 : 2) : (f32 ? 2 : 1);
+    minb = k == 3 ? (stride == 1 ? 4 : 5) : 3;
+    rows = Fo; cols = To;
+  } else if (kind == 1) {                            // launch_wg_slide
+    if (k == 5 && !f32) { eat_set_error("dw_plan: the bf16 5x5 weight gradient uses the tile kernel"); return EAT_ERR_UNSUPPORTED; }
+    V = f32 ? (k == 5 ? 2 : 4) : 8;
+    P = f32 ? 4 : 1;
+    minb = 3;
+    rows = Fo; cols = To;
+  } else if (kind == 2) {                            // launch_dg2_slide: pairs of din rows, 4 din columns per strip
+    if (stride != 2) { eat_set_error("dw_plan: kind 2 is the stride-2 data gradient"); return EAT_ERR_ARG; }
+    P = 4; minb = k == 3 ? 4 : 3;
+    rows = (F + 1) / 2; cols = T; S = 1; Kp = (k + 1) / 2;
+  } else {
+    eat_set_error("dw_plan: kind must be 0, 1 or 2");
+    return EAT_ERR_ARG;
+  }
+  const SlidePlan pl = plan_slide(B, rows, cols, C / V, V, P, S, Kp, minb, per_sample != 0);
+  plan[0] = pl.chunks; plan[1] = pl.cvc; plan[2] = pl.seg_rows; plan[3] = pl.groups; plan[4] = pl.gy; plan[5] = P;
+  return EAT_OK;
+}

@@ -45,6 +45,13 @@ extern "C" {
 
 const char* eat_last_error(void);
 int eat_abi_version(void);
+
+/* Host-only (no GPU work): the launch plan of the sliding-window depthwise kernels (csrc/dw_slide.cu) for a layer.
+ * kind: 0 forward, 1 weight gradient, 2 stride-2 data gradient.  per_sample != 0: blockIdx.y must be the sample
+ * (squeeze-excitation pooling, DynamicConv per-sample weights).  plan[6] = {channel chunks, channel vectors per chunk,
+ * output rows (row pairs for kind 2) per segment, CTA groups per chunk, gridDim.y, strip width}.  Exposed so the
+ * host logic is testable without a device (tests/test_cabi.py). */
+int eat_dw_plan(int kind, int dtype, int B, int F, int T, int C, int k, int stride, int per_sample, int* plan);
 int eat_device_check(int device);
 
 /* Fused log-mel front end.  Replaces AugmentMelSTFT.forward, models/preprocess.py:40-67

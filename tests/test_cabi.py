@@ -4,6 +4,8 @@ import os
 import re
 import subprocess
 
+import pytest
+
 from efficientat_b200 import _lib
 
 
@@ -38,3 +40,44 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f"{f} imports the oracle"
+
+
+def test_depthwise_launch_plan_host_logic():
+    """eat_dw_plan (host only): the sliding-window kernels' launch plan covers every channel, keeps all CTAs resident,
+    and at the bench batch size loses little to the rounding of units per thread."""
+    import ctypes
+    from efficientat_b200._lib import lib
+    L = lib()
+    plan = (ctypes.c_int * 6)()
+    shapes = [(64, 500, 16, 3, 1), (64, 500, 64, 3, 2), (32, 250, 72, 3, 1), (32, 250, 72, 5, 2), (16, 125, 120, 5, 1),
+              (16, 125, 240, 3, 2), (8, 63, 200, 3, 1), (8, 63, 672, 5, 2), (4, 32, 960, 5, 1), (1, 9, 32, 3, 1), (5, 3, 2560, 5, 2)]
+    for kind in (0, 1, 2):
+        for dtype in (0, 1):
+            for B in (1, 8, 256):
+                for per_sample in (0, 1):
+                    for (F, T, C, k, s) in shapes:
+                        if kind == 2 and s != 2:
+                            continue
+                        if kind == 1 and k == 5 and dtype == 1:
+                            with pytest.raises(RuntimeError):
+                                L.dw_plan(kind, dtype, B, F, T, C, k, s, per_sample, ctypes.addressof(plan))
+                            continue
+                        L.dw_plan(kind, dtype, B, F, T, C, k, s, per_sample, ctypes.addressof(plan))
+                        chunks, cvc, seg, groups, gy, P = list(plan)
+                        V = (8 if dtype else 4) if not (kind == 1 and k == 5) else 2
+                        pad = (k - 1) // 2
+                        Fo, To = (F + 2 * pad - k) // s + 1, (T + 2 * pad - k) // s + 1
+                        rows, cols = ((F + 1) // 2, T) if kind == 2 else (Fo, To)
+                        assert chunks >= 1 and cvc >= 1 and chunks * cvc >= C // V and cvc * V <= 512 and cvc <= 128
+                        assert 1 <= seg <= max(rows, 1) and groups >= 1 and gy >= 1 and P in (1, 2, 4)
+                        assert chunks * groups * gy <= 148 * 5 or per_sample      # one resident wave unless blockIdx.y = sample
+                        if per_sample:
+                            assert gy == B
+                        if B == 256 and not per_sample and F >= 4 and T >= 32:
+                            ppb = max(1, 128 // cvc)
+                            units = -(-cols // P) * -(-rows // seg) * B
+                            slots = groups * gy * ppb
+                            rounds = -(-units // slots)
+                            assert rounds * slots <= 1.34 * units, (kind, dtype, (F, T, C, k, s), list(plan), rounds * slots / units)
+    with pytest.raises(RuntimeError):
+        L.dw_plan(0, 0, 1, 8, 8, 6, 3, 1, 0, ctypes.addressof(plan))       # channels not a multiple of the vector width
