@@ -110,9 +110,32 @@ def cpu_reference_step_factory(batch, width=1.0):
     return step
 
 
-def time_cpu_reference(batch, steps, warmup):
-    cores = os.cpu_count() or 1
+def usable_cores():
+    """host threads this process may actually use: scheduler affinity, capped by the cgroup CPU quota if there is one"""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
+def time_cpu_reference(batch, steps, warmup, budget_s=150.0):
+    """-> (clips/s, s/step, threads, clips per step).  The per-step sample is bounded: a one-clip calibration step
+    (which is also a warm-up) sets the clips per step so that warm-up + timed steps stay within `budget_s`."""
+    cores = usable_cores()
     torch.set_num_threads(cores)
+    one = cpu_reference_step_factory(1)
+    one()                                                   # first call pays allocator / thread-pool start-up
+    t0 = time.perf_counter()
+    one()
+    t1 = time.perf_counter() - t0                           # seconds per clip, roughly
+    batch = max(1, min(batch, int(budget_s / max(t1 * (steps + max(1, warmup)), 1e-6))))
     step = cpu_reference_step_factory(batch)
     for _ in range(max(1, warmup)):
         step()
@@ -120,7 +143,7 @@ def time_cpu_reference(batch, steps, warmup):
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps, cores
+    return batch * steps / dt, dt / steps, cores, batch
 
 
 def run_reference_arm(args):
@@ -129,8 +152,7 @@ def run_reference_arm(args):
         return
     k = min(args.steps, 5)
     w = min(args.warmup, 1)
-    b = args.cpu_baseline_batch
-    value, s_per_step, cores = time_cpu_reference(b, k, w)
+    value, s_per_step, cores, b = time_cpu_reference(args.cpu_baseline_batch, k, w)
     sample = f"{k} steps x {b} clips (mel+fwd+bwd+Adam, fp32, oracle port of the reference modules)"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": args.gpus,
             "steps": k, "warmup": w, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -413,9 +435,9 @@ def run_ours(args):
             "loss": [float(v) for v in loss_host.tolist()],
         }
         if not args.no_cpu_baseline and world == 1:
-            v, s_per_step, cores = time_cpu_reference(args.cpu_baseline_batch, 2, 1)
+            v, s_per_step, cores, cb = time_cpu_reference(args.cpu_baseline_batch, 2, 1, budget_s=45.0)
             line["cpu_baseline"] = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
-                                    "sample": f"2 steps x {args.cpu_baseline_batch} clips, same training step, fp32, "
+                                    "sample": f"2 steps x {cb} clips, same training step, fp32, "
                                               "oracle port of the reference modules on the host cores"}
         print(json.dumps(line), flush=True)
     if world > 1:
