@@ -106,7 +106,7 @@ def cpu_reference_step_factory(batch, width=1.0):
         opt.zero_grad()
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
     return step
 
 
