@@ -68,6 +68,22 @@ class _Lib:
         return call
 
 
+def check_module_tensors(module, device, what):
+    """The kernels take raw `data_ptr()`s as `float*`: every parameter and buffer handed to them must be an fp32 (int64
+    for BatchNorm's step counter), contiguous tensor on the input's CUDA device.  A forgotten `.to(device)`,
+    `model.half()` or `.double()` raises here instead of dereferencing a host pointer / wrong-width data."""
+    import itertools
+    import torch
+    for name, t in itertools.chain(module.named_parameters(), module.named_buffers()):
+        ok_dtype = t.dtype == torch.float32 or (not t.is_floating_point())
+        if t.device != device or not ok_dtype or not t.is_contiguous():
+            raise RuntimeError(
+                f"{what}: tensor '{name}' is {t.dtype} on {t.device}{'' if t.is_contiguous() else ' (non-contiguous)'}; "
+                f"the sm_100a kernels need contiguous fp32 tensors on {device} (the input's device). "
+                "Call module.to(device) / keep parameters in fp32 (bf16 activation storage is selected with "
+                "get_model(precision='bf16'), not with .half()/.bfloat16()).")
+
+
 _lib = None
 
 

@@ -14,6 +14,21 @@
 
 void eat_set_error(const char* msg);
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: remember it per (kernel instantiation, device)
+// so that a process driving several GPUs opts every one of them in.  `mask` is a function-local static of the caller.
+template <typename K>
+inline int eat_opt_in_smem(K kernel, size_t bytes, unsigned long long& mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { eat_set_error("cudaGetDevice failed"); return EAT_ERR_CUDA; }
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(mask & bit)) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) { eat_set_error(cudaGetErrorString(e)); return EAT_ERR_CUDA; }
+    mask |= bit;
+  }
+  return EAT_OK;
+}
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 

@@ -218,11 +218,8 @@ extern "C" int eat_mel_fwd(const float* wave, int B, int N, const float* window,
   p.max_len = max_len; p.preemph = preemph; p.log_offset = 1e-5f; p.out_add = 4.5f; p.out_div = 5.f;
   size_t smem = 1024 * sizeof(float2) + kNfft * sizeof(float) + kGroups * kHalf * sizeof(float2) +
                 kGroups * 516 * sizeof(float) + (size_t)n_mels * 33 * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    attr_set = true;
-  }
+  static unsigned long long attr_mask = 0;
+  if (int rc = eat_opt_in_smem(mel_kernel, 160 * 1024, attr_mask)) return rc;
   dim3 grid(ceil_div(p.T, kFramesPerCta), B);
   mel_kernel<<<grid, kThreads, smem, stream>>>(p);
   EAT_CHECK_LAUNCH();

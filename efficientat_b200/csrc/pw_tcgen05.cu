@@ -585,12 +585,8 @@ int launch_tc_x(const TcParams& p0, cudaStream_t st) {
                           2 * BN_MAX * sizeof(float) + 16 * BN_MAX * sizeof(float) +
                           (2 * STAGES + 4) * sizeof(uint64_t) + 16;
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(pw_tc_kernel<T, NP, STAGES, BN_MAX, DYN, EPI, XACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { eat_set_error(cudaGetErrorString(e)); return EAT_ERR_CUDA; }
-    attr_done = true;
-  }
+  static unsigned long long attr_mask = 0;
+  if (int rc = eat_opt_in_smem(pw_tc_kernel<T, NP, STAGES, BN_MAX, DYN, EPI, XACT>, smem, attr_mask)) return rc;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

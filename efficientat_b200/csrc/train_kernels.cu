@@ -29,11 +29,15 @@ __device__ __forceinline__ float bce_logits(float z, float t) {
   return fmaxf(z, 0.f) - z * t + log1pf(expf(-fabsf(z)));
 }
 
-// loss = kd * mean BCE(z, y_mix) + (1 - kd) * mean BCE(z, t_mix), with *_mix the mixup blend of row b and
-// row perm[b]; dlogits = (sigmoid(z) - (kd * y_mix + (1 - kd) * t_mix)) / (B * C).
+// loss = kd * mean BCE(z, y_mix) + (1 - kd) * mean_b known[b] * BCE(z, t_mix), with *_mix the mixup blend of row b
+// and row perm[b] (BCE is linear in the target, so blending the targets equals blending the two losses as
+// ex_audioset.py:170-174 does); known[b] = 0 zeroes the WHOLE distillation row of a clip without teacher predictions
+// (ex_audioset.py:166-178: `soft_targets_loss[unknown_indices] *= 0` before the mean over all B rows).
+// dlogits = (kd * (sigmoid(z) - y_mix) + (1 - kd) * known[b] * (sigmoid(z) - t_mix)) / (B * C).
 // loss_acc[0] += label term (already weighted), loss_acc[1] += distillation term (weighted).
 __global__ void bce_kd_kernel(const float* __restrict__ z, const float* __restrict__ y, const float* __restrict__ teacher,
-                              const int* __restrict__ perm, const float* __restrict__ lam, float kd, int B, int C,
+                              const float* __restrict__ known, const int* __restrict__ perm,
+                              const float* __restrict__ lam, float kd, int B, int C,
                               float* __restrict__ dz, double* __restrict__ loss_acc) {
   const long long n = (long long)B * C;
   const float inv = 1.f / (float)n;
@@ -44,14 +48,16 @@ __global__ void bce_kd_kernel(const float* __restrict__ z, const float* __restri
     const int pb = perm != nullptr ? perm[b] : b;
     const float zz = z[i];
     const float ym = y[i] * l + y[(size_t)pb * C + c] * (1.f - l);
-    float target = ym;
+    const float sg = sigmoidf_(zz);
+    float grad = sg - ym;
     l_hard += bce_logits(zz, ym);
     if (teacher != nullptr) {
+      const float kn = known != nullptr ? known[b] : 1.f;
       const float tm = teacher[i] * l + teacher[(size_t)pb * C + c] * (1.f - l);
-      l_soft += bce_logits(zz, tm);
-      target = kd * ym + (1.f - kd) * tm;
+      l_soft += kn * bce_logits(zz, tm);
+      grad = kd * (sg - ym) + (1.f - kd) * kn * (sg - tm);
     }
-    if (dz != nullptr) dz[i] = (sigmoidf_(zz) - target) * inv;
+    if (dz != nullptr) dz[i] = grad * inv;
   }
   l_hard = warp_sum(l_hard);
   l_soft = warp_sum(l_soft);
@@ -94,11 +100,13 @@ int eat_mixup(const float* x, const int* perm, const float* lam, float* out, int
   return EAT_OK;
 }
 
-int eat_bce_kd_loss(const float* logits, const float* y, const float* teacher, const int* perm, const float* lam,
-                    float kd_lambda, int B, int C, float* dlogits, double* loss_acc, cudaStream_t st) {
+int eat_bce_kd_loss(const float* logits, const float* y, const float* teacher, const float* teacher_known,
+                    const int* perm, const float* lam, float kd_lambda, int B, int C, float* dlogits, double* loss_acc,
+                    cudaStream_t st) {
   if (B == 0) return EAT_OK;
+  if (kd_lambda < 0.f || kd_lambda > 1.f) { eat_set_error("bce_kd_loss: kd_lambda must be in [0, 1] (ex_audioset.py:100)"); return EAT_ERR_ARG; }
   int grid = (int)min((long long)148 * 2, ceil_div_ll((long long)B * C, 256));
-  bce_kd_kernel<<<grid, 256, 0, st>>>(logits, y, teacher, perm, lam, kd_lambda, B, C, dlogits, loss_acc);
+  bce_kd_kernel<<<grid, 256, 0, st>>>(logits, y, teacher, teacher_known, perm, lam, kd_lambda, B, C, dlogits, loss_acc);
   EAT_CHECK_LAUNCH();
   return EAT_OK;
 }

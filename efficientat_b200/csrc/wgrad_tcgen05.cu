@@ -311,12 +311,8 @@ int launch_wg(const WgParams& p0, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * NP * (MB * G_ATOMS * 128 + MB * (KT_MAX / 64) * 128) +
                           4 * 32 * STG_LD * sizeof(float) + (2 * STAGES + 1) * sizeof(uint64_t) + 16;
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<T, NP, STAGES, KT_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { eat_set_error(cudaGetErrorString(e)); return EAT_ERR_CUDA; }
-    attr_done = true;
-  }
+  static unsigned long long attr_mask = 0;
+  if (int rc = eat_opt_in_smem(wgrad_tc_kernel<T, NP, STAGES, KT_MAX>, smem, attr_mask)) return rc;
   wgrad_tc_kernel<T, NP, STAGES, KT_MAX><<<tiles * splits, kThreads, smem, st>>>(p);
   EAT_CHECK_LAUNCH();
   return EAT_OK;

@@ -17,7 +17,7 @@ import os
 
 import torch
 
-from ._lib import lib
+from ._lib import check_module_tensors, lib
 
 ACT = {"none": 0, "relu": 1, "hswish": 2}
 BN_EPS = 1e-3
@@ -183,17 +183,20 @@ class MNEngine:
             raise RuntimeError("efficientat_b200 models run on CUDA (sm_100a) only; got a CPU tensor")
         if x.dim() != 4 or x.shape[1] != 1:
             raise ValueError(f"expected input of shape [B, 1, F, T], got {tuple(x.shape)}")
+        check_module_tensors(self.model, x.device, type(self.model).__name__)
+        self.dropout_p = float(self.model.classifier[4].p)          # read at call time (it may be changed after engine())
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters())
-        if self.model.training:
-            if return_fmaps:
-                raise NotImplementedError("return_fmaps is available in eval mode only")
-            from .autograd import mn_train_forward
-            logits, feat = mn_train_forward(self, x, needs_grad)
-            return self._squeeze(logits, feat) + (None,)
-        if needs_grad and x.requires_grad:
-            raise NotImplementedError("gradients w.r.t. the input spectrogram are not implemented")
-        logits, feat, fmaps = self._forward_eval(x.detach(), return_fmaps)
-        return self._squeeze(logits, feat) + (fmaps,)
+        with torch.cuda.device(x.device):                            # launches go to x's device, whatever is current
+            if self.model.training:
+                if return_fmaps:
+                    raise NotImplementedError("return_fmaps is available in eval mode only")
+                from .autograd import mn_train_forward
+                logits, feat = mn_train_forward(self, x, needs_grad)
+                return self._squeeze(logits, feat) + (None,)
+            if needs_grad and x.requires_grad:
+                raise NotImplementedError("gradients w.r.t. the input spectrogram are not implemented")
+            logits, feat, fmaps = self._forward_eval(x.detach(), return_fmaps)
+            return self._squeeze(logits, feat) + (fmaps,)
 
     @staticmethod
     def _squeeze(logits, feat):

@@ -9,7 +9,7 @@ the bank gradients (sum_b alpha S_b) and the attention gradients (<S_b, W_k>) fo
 reductions, the coefficient / attention / coordinate nets, and the ContextGen pooling."""
 import torch
 
-from ._lib import lib
+from ._lib import check_module_tensors, lib
 from .engine import ACT, MNEngine, _Layer, _conv_out, _ptr, _stream
 
 
@@ -46,15 +46,51 @@ class DyMNEngine(MNEngine):
             raise RuntimeError("efficientat_b200 models run on CUDA (sm_100a) only; got a CPU tensor")
         if x.dim() != 4 or x.shape[1] != 1:
             raise ValueError(f"expected input of shape [B, 1, F, T], got {tuple(x.shape)}")
-        if self.model.training:
-            if return_fmaps:
-                raise NotImplementedError("return_fmaps is available in eval mode only")
-            needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters())
-            from .autograd import mn_train_forward
-            logits, feat = mn_train_forward(self, x, needs_grad)
-            return logits, feat, None
-        logits, feat, fmaps = self._forward_eval(x.detach(), return_fmaps)
-        return logits, feat, fmaps
+        check_module_tensors(self.model, x.device, type(self.model).__name__)
+        self.dropout_p = float(self.model.classifier[4].p)
+        with torch.cuda.device(x.device):
+            if self.model.training:
+                if return_fmaps:
+                    raise NotImplementedError("return_fmaps is available in eval mode only")
+                needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters())
+                from .autograd import mn_train_forward
+                logits, feat = mn_train_forward(self, x, needs_grad)
+                return logits, feat, None
+            logits, feat, fmaps = self._forward_eval(x.detach(), return_fmaps)
+            return logits, feat, fmaps
+
+    # ------------------------------------------------------------------ DynamicConv 1x1 dispatch
+    def _mixed_weights(self, W, att, B, n):
+        """[B, n] per-sample kernels sum_k att[b,k] W[k] (dy_block.py:111-117), exact fp32 (cross-check route only)"""
+        nk = att.shape[1]
+        out = torch.empty(B, n, device=att.device, dtype=torch.float32)
+        lib().gemm_simt_fwd(att.data_ptr(), 0, W.data_ptr(), 1, out.data_ptr(), 0, B, n, nk, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0,
+                            _stream())
+        return out
+
+    def _dyn_gemm(self, A, W, att, nk, C, M, N, K, rps, sc=None, act=0, res=None, stats=None):
+        """C[M,N] = epi(A[M,K] . (sum_k att[b,k] W_k)[N,K]^T), rows of sample b use its own mixed kernel.
+        Default: tcgen05 kernel with the mix fused into the weight staging.  EAT_GEMM=simt: the reference's own order
+        of operations in exact fp32 (materialise the per-sample kernels, one CUDA-core GEMM per sample) -- the
+        independent implementation the tensor-core path is checked against."""
+        L = lib()
+        dc = self.dcode
+        if self.gemm_impl != "simt":
+            L.pw_tc_dyn_fwd(A.data_ptr(), dc, W.data_ptr(), att.data_ptr(), nk, C.data_ptr(), M, N, K, rps, 0, 0, 0,
+                            _ptr(sc[0]) if sc is not None else 0, _ptr(sc[1]) if sc is not None else 0, act, _ptr(res),
+                            _ptr(stats[0]) if stats is not None else 0, _ptr(stats[1]) if stats is not None else 0,
+                            _stream())
+            return
+        B = M // rps
+        Wm = self._mixed_weights(W, att, B, N * K)
+        es = 4 if dc == 0 else 2
+        for b in range(B):
+            L.gemm_simt_fwd(A.data_ptr() + b * rps * K * es, dc, Wm.data_ptr() + 4 * b * N * K, 0,
+                            C.data_ptr() + b * rps * N * es, dc, rps, N, K, 0, 0, 0, 0, 1,
+                            _ptr(sc[0]) if sc is not None else 0, _ptr(sc[1]) if sc is not None else 0, act,
+                            (res.data_ptr() + b * rps * N * es) if res is not None else 0,
+                            _ptr(stats[0]) if stats is not None else 0, _ptr(stats[1]) if stats is not None else 0,
+                            _stream())
 
     # ------------------------------------------------------------------
     def _dy_block_eval(self, blk, a, B, Fi, Ti):
@@ -100,9 +136,8 @@ class DyMNEngine(MNEngine):
             att = attention(m.exp_conv)
             sc = self._fold(m.exp_norm, dev)
             e = torch.empty(B, Fi, Ti, blk.cexp, device=dev, dtype=td)
-            L.pw_tc_dyn_fwd(inp.data_ptr(), dc, m.exp_conv.weight.data_ptr(), att.data_ptr(), m.exp_conv.k, e.data_ptr(),
-                            B * Fi * Ti, blk.cexp, blk.cin, Fi * Ti, 0, 0, 0, sc[0].data_ptr(), sc[1].data_ptr(), blk.act,
-                            0, 0, 0, st)
+            self._dyn_gemm(inp, m.exp_conv.weight, att, m.exp_conv.k, e, B * Fi * Ti, blk.cexp, blk.cin, Fi * Ti, sc=sc,
+                           act=blk.act)
         else:
             e = inp
         # ---- depthwise DynamicConv + BN + DyReLU-B + CoordAtt
@@ -123,9 +158,8 @@ class DyMNEngine(MNEngine):
         att = attention(m.proj_conv)
         sc = self._fold(m.proj_norm, dev)
         o = torch.empty(B, Fo, To, blk.cout, device=dev, dtype=td)
-        L.pw_tc_dyn_fwd(d.data_ptr(), dc, m.proj_conv.weight.data_ptr(), att.data_ptr(), m.proj_conv.k, o.data_ptr(),
-                        B * Fo * To, blk.cout, blk.cexp, Fo * To, 0, 0, 0, sc[0].data_ptr(), sc[1].data_ptr(), 0,
-                        _ptr(inp) if blk.res else 0, 0, 0, st)
+        self._dyn_gemm(d, m.proj_conv.weight, att, m.proj_conv.k, o, B * Fo * To, blk.cout, blk.cexp, Fo * To, sc=sc,
+                       res=inp if blk.res else None)
         return o, Fo, To
 
     def _forward_eval(self, x, return_fmaps=False):
@@ -207,9 +241,7 @@ class DyMNEngine(MNEngine):
             att_e = attention(m.exp_conv)
             z1 = torch.empty(B, Fi, Ti, blk.cexp, device=dev, dtype=td)
             stt = self._new_stats(blk.cexp, dev)
-            L.pw_tc_dyn_fwd(inp.data_ptr(), dc, m.exp_conv.weight.data_ptr(), att_e.data_ptr(), m.exp_conv.k,
-                            z1.data_ptr(), M, blk.cexp, blk.cin, Fi * Ti, 0, 0, 0, 0, 0, 0, 0, stt[0].data_ptr(),
-                            stt[1].data_ptr(), st)
+            self._dyn_gemm(inp, m.exp_conv.weight, att_e, m.exp_conv.k, z1, M, blk.cexp, blk.cin, Fi * Ti, stats=stt)
             sc1, sv1 = self._finalize(m.exp_norm, stt, M, dev)
             R.update(att_e=att_e, z1=z1, sc1=sc1, sv1=sv1)
             dw_in, dw_sc = z1, sc1
@@ -237,8 +269,7 @@ class DyMNEngine(MNEngine):
         att_p = attention(m.proj_conv)
         z3 = torch.empty(B, Fo, To, blk.cout, device=dev, dtype=td)
         stt = self._new_stats(blk.cout, dev)
-        L.pw_tc_dyn_fwd(p.data_ptr(), dc, m.proj_conv.weight.data_ptr(), att_p.data_ptr(), m.proj_conv.k, z3.data_ptr(),
-                        Mo, blk.cout, blk.cexp, Fo * To, 0, 0, 0, 0, 0, 0, 0, stt[0].data_ptr(), stt[1].data_ptr(), st)
+        self._dyn_gemm(p, m.proj_conv.weight, att_p, m.proj_conv.k, z3, Mo, blk.cout, blk.cexp, Fo * To, stats=stt)
         sc3, sv3 = self._finalize(m.proj_norm, stt, Mo, dev)
         out = torch.empty(B, Fo, To, blk.cout, device=dev, dtype=td)
         L.bn_apply(z3.data_ptr(), sc3[0].data_ptr(), sc3[1].data_ptr(), 0, _ptr(inp) if blk.res else 0, out.data_ptr(),
@@ -256,6 +287,8 @@ class DyMNEngine(MNEngine):
         M = B * rps
         nb = conv.k
         W = conv.weight
+        if self.gemm_impl == "simt":
+            return self._dyn1x1_bwd_exact(conv, Gt, X, att, B, rps, N, K, G, res)
         Wt = torch.empty(nb, K, N, device=dev, dtype=torch.float32)           # W_k^T banks for the data gradient
         for j in range(nb):
             L.transpose_f32(W.data_ptr() + 4 * j * N * K, Wt.data_ptr() + 4 * j * N * K, N, K, st)
@@ -264,6 +297,26 @@ class DyMNEngine(MNEngine):
                         _ptr(res), 0, 0, st)
         S = torch.zeros(B, N * K, device=dev, dtype=torch.float32)             # per-sample weight gradients
         L.pw_tc_wgrad_persample(Gt.data_ptr(), X.data_ptr(), dc, S.data_ptr(), M, N, K, rps, st)
+        datt = torch.empty(B, nb, device=dev, dtype=torch.float32)
+        L.dyn_wgrad_mix(S.data_ptr(), att.data_ptr(), W.data_ptr(), G[W].data_ptr(), datt.data_ptr(), B, N * K, nb, st)
+        return dX, datt
+
+    def _dyn1x1_bwd_exact(self, conv, Gt, X, att, B, rps, N, K, G, res):
+        """exact-fp32 cross-check of _dyn1x1_bwd: per-sample CUDA-core GEMMs on the materialised mixed kernels"""
+        L = lib()
+        st = _stream()
+        dev = Gt.device
+        dc = self.dcode
+        es = 4 if dc == 0 else 2
+        M, nb, W = B * rps, conv.k, conv.weight
+        Wm = self._mixed_weights(W, att, B, N * K)
+        dX = torch.empty(M, K, device=dev, dtype=self.tdtype)
+        S = torch.zeros(B, N * K, device=dev, dtype=torch.float32)
+        for b in range(B):
+            g_b, x_b = Gt.data_ptr() + b * rps * N * es, X.data_ptr() + b * rps * K * es
+            L.gemm_simt_fwd(g_b, dc, Wm.data_ptr() + 4 * b * N * K, 1, dX.data_ptr() + b * rps * K * es, dc, rps, K, N,
+                            0, 0, 0, 0, 1, 0, 0, 0, (res.data_ptr() + b * rps * K * es) if res is not None else 0, 0, 0, st)
+            L.gemm_simt_wgrad(g_b, dc, x_b, dc, S.data_ptr() + 4 * b * N * K, 0, rps, N, K, 0, 0, 0, 0, 1, st)
         datt = torch.empty(B, nb, device=dev, dtype=torch.float32)
         L.dyn_wgrad_mix(S.data_ptr(), att.data_ptr(), W.data_ptr(), G[W].data_ptr(), datt.data_ptr(), B, N * K, nb, st)
         return dX, datt

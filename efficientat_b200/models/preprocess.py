@@ -8,14 +8,19 @@ import math
 import torch
 import torch.nn as nn
 
-from .._lib import lib
+from .._lib import check_module_tensors, lib
 from .filterbank import kaldi_mel_banks, to_bands
 
 
 class _AxisMasking(nn.Module):
-    """torchaudio.transforms.{Frequency,Time}Masking(param, iid_masks=True) on [B, F, T]:
-    one band per example, width ~ U[0, param), start ~ U[0, size - width), filled with 0.0
-    (models/preprocess.py:31-38, applied :61-63 in training only)."""
+    """torchaudio.transforms.{Frequency,Time}Masking(param, iid_masks=True) on [B, F, T]
+    (models/preprocess.py:31-38, applied :61-63 in training only): one band per example, width ~ U[0, param),
+    start ~ U[0, size - width), filled with 0.0, drawn with torch.rand on the spectrogram's DEVICE generator.
+    This is the behaviour of torchaudio >= 2.1 (`mask_along_axis_iid` over all leading dimensions), i.e. of the
+    installed 2.11 that serves as the oracle here.  The reference's requirements.txt pins torchaudio 0.13, where
+    iid masking required a 4-D input and a 3-D spectrogram got ONE mask shared by the batch from the CPU generator;
+    that older behaviour is NOT reproduced.  Both scripts' defaults are freqm = timem = 0 (ex_audioset.py:380-381),
+    for which the module is an Identity and no random number is drawn."""
 
     def __init__(self, mask_param, axis):
         super().__init__()
@@ -92,7 +97,12 @@ class AugmentMelSTFT(nn.Module):
             raise RuntimeError("efficientat_b200.AugmentMelSTFT runs on CUDA (sm_100a) only; got a CPU tensor")
         if x.dim() != 2:
             raise ValueError(f"expected waveform of shape [B, N], got {tuple(x.shape)}")
+        check_module_tensors(self, x.device, "AugmentMelSTFT")
         x = x.float().contiguous()
+        with torch.cuda.device(x.device):
+            return self._forward(x)
+
+    def _forward(self, x):
         # the reference draws both randints on every call, eval included (preprocess.py:45-46)
         fmin = self.fmin + torch.randint(self.fmin_aug_range, (1,)).item()
         fmax = self.fmax + self.fmax_aug_range // 2 - torch.randint(self.fmax_aug_range, (1,)).item()

@@ -60,12 +60,23 @@ class HostPrefetcher:
 
 
 class AudioSetTrainer:
+    """The body of the reference's training loop (ex_audioset.py:120-201) on device-resident tensors.
+
+    lr schedule: `schedule` is the reference's epoch -> factor lambda (helpers/utils.py:56-84, built by
+    `exp_warmup_linear_down`); the learning rate of epoch e is `lr * schedule(e)`, which is what
+    `LambdaLR` + one `scheduler.step()` per epoch give (ex_audioset.py:95-97,201).  `set_epoch(e)` also forwards to
+    `model.update_params(e)` (DyMN temperature schedule, ex_audioset.py:132-133)."""
+
     def __init__(self, model, mel, lr=8e-4, kd_lambda=0.1, mixup_alpha=0.3, weight_decay=0.0, adamw=False,
-                 betas=(0.9, 0.999), eps=1e-8, process_group=None, cuda_graph=False):
+                 betas=(0.9, 0.999), eps=1e-8, process_group=None, cuda_graph=False, schedule=None):
+        if not 0.0 <= kd_lambda <= 1.0:
+            raise AssertionError("Lambda for Knowledge Distillation must be between 0 and 1.")     # ex_audioset.py:100
         self.model, self.mel = model, mel
         self.engine = model.engine()
         self.lr, self.kd_lambda, self.mixup_alpha = lr, kd_lambda, mixup_alpha
         self.weight_decay, self.adamw, self.betas, self.eps = weight_decay, adamw, betas, eps
+        self.schedule = schedule
+        self.epoch = 0
         self.pg = process_group
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
@@ -75,12 +86,32 @@ class AudioSetTrainer:
         self.cuda_graph = cuda_graph
         self._graphs = {}
 
+    # ------------------------------------------------------------------ schedule
+    def current_lr(self):
+        return self.lr * (self.schedule(self.epoch) if self.schedule is not None else 1.0)
+
+    def set_epoch(self, epoch):
+        """start of epoch `epoch`: learning rate of the LambdaLR schedule + DyMN temperature update"""
+        self.epoch = int(epoch)
+        if hasattr(self.model, "update_params"):
+            import contextlib
+            import io
+            with contextlib.redirect_stdout(io.StringIO()):          # the reference prints one line per DynamicConv
+                self.model.update_params(self.epoch)
+
     def _flatten(self):
         """Re-point every parameter into one contiguous fp32 arena (order = model.parameters()), so the
         optimiser is one kernel and the gradient all-reduce one collective.  state_dict()/load_state_dict()
-        keep working (they copy in place)."""
+        keep working (they copy in place).  With world > 1 the replicas start from rank 0's parameters AND
+        buffers (DistributedDataParallel's constructor broadcast; ex_pl_audioset.py:287-293)."""
         params = self.engine.param_list()
         dev = params[0].device
+        for p in params:
+            if p.device != dev or p.dtype != torch.float32:
+                raise RuntimeError("AudioSetTrainer: all parameters must be fp32 tensors on one CUDA device "
+                                   f"(got {p.dtype} on {p.device}); call model.to(device) first")
+        if dev.type != "cuda":
+            raise RuntimeError("AudioSetTrainer: the model must be on a CUDA device (no CPU fallback)")
         n = sum(p.numel() for p in params)
         flat = torch.empty(n, device=dev, dtype=torch.float32)
         off = 0
@@ -92,20 +123,46 @@ class AudioSetTrainer:
         self.flat_p = flat
         self.exp_avg = torch.zeros_like(flat)
         self.exp_avg_sq = torch.zeros_like(flat)
-        if self.world > 1:        # replicas start from rank 0's parameters (DDP constructor semantics)
+        if self.world > 1:
             torch.distributed.broadcast(self.flat_p, 0, group=self.pg)
+            for b in self.model.buffers():
+                torch.distributed.broadcast(b, 0, group=self.pg)
 
-    def forward_backward(self, wave, y, teacher=None, perm=None, lam=None):
-        """-> (loss_acc fp64[2] device = weighted label / distillation losses, flat gradient arena)."""
+    # ------------------------------------------------------------------ one step
+    @staticmethod
+    def _check_targets(t, B, name, dev):
+        if t is None:
+            return None
+        if t.dim() != 2 or t.shape[0] != B:
+            raise ValueError(f"{name} must have shape [B, num_classes] with B = {B}, got {tuple(t.shape)}")
+        if t.device != dev:
+            raise RuntimeError(f"{name} must be on {dev}, got {t.device}")
+        return t.to(torch.float32).contiguous()
+
+    def forward_backward(self, wave, y, teacher=None, perm=None, lam=None, teacher_known=None):
+        """-> (loss_acc fp64[2] device = weighted label / distillation losses, flat gradient arena).
+        teacher_known: optional [B] bool/float, False/0 for clips without teacher predictions (their distillation
+        loss is zeroed, ex_audioset.py:166-178)."""
         L = lib()
         st = _stream()
         B = wave.shape[0]
         spec = self.mel(wave.reshape(B, -1))                       # [B, n_mels, T]
+        dev = spec.device
+        y = self._check_targets(y, B, "y", dev)
+        teacher = self._check_targets(teacher, B, "teacher", dev)
+        if teacher is not None and teacher.shape != y.shape:
+            raise ValueError(f"teacher {tuple(teacher.shape)} and y {tuple(y.shape)} must have the same shape")
+        if teacher_known is not None:
+            if teacher is None:
+                raise ValueError("teacher_known given without teacher predictions")
+            teacher_known = teacher_known.to(device=dev, dtype=torch.float32).contiguous().view(B)
+        if self.kd_lambda <= 0:                                    # ex_audioset.py:159,183: no distillation term at all
+            teacher = teacher_known = None
         if self.mixup_alpha and perm is None:
             perm, lam = draw_mixup(B, self.mixup_alpha)
         if perm is not None:
-            perm_d = perm.to(dtype=torch.int32).to(device=spec.device, non_blocking=True)
-            lam_d = lam.to(dtype=torch.float32).to(device=spec.device, non_blocking=True)
+            perm_d = perm.to(dtype=torch.int32).to(device=dev, non_blocking=True)
+            lam_d = lam.to(dtype=torch.float32).to(device=dev, non_blocking=True)
             mixed = torch.empty_like(spec)
             L.mixup(spec.data_ptr(), perm_d.data_ptr(), lam_d.data_ptr(), mixed.data_ptr(), B,
                     spec.shape[1] * spec.shape[2], st)
@@ -113,43 +170,56 @@ class AudioSetTrainer:
         else:
             perm_d = lam_d = None
         if self.cuda_graph:
-            return self._graph_fwd_bwd(spec, y, teacher, perm_d, lam_d)
-        return self._core(spec.unsqueeze(1), y, teacher, perm_d, lam_d)
+            return self._graph_fwd_bwd(spec, y, teacher, perm_d, lam_d, teacher_known)
+        return self._core(spec.unsqueeze(1), y, teacher, perm_d, lam_d, teacher_known)
 
-    def _core(self, spec4, y, teacher, perm_d, lam_d):
+    def _core(self, spec4, y, teacher, perm_d, lam_d, known=None):
         """model forward + loss + backward on device tensors -> (loss_acc, flat gradient arena)"""
         L = lib()
         B = spec4.shape[0]
         logits, _, saved = self.engine._forward_train(spec4)
         dlogits = torch.empty_like(logits)
         loss_acc = torch.zeros(2, device=spec4.device, dtype=torch.float64)
+        # without a teacher the label loss carries weight 1 (ex_audioset.py:182-183)
         L.bce_kd_loss(logits.data_ptr(), y.data_ptr(), teacher.data_ptr() if teacher is not None else 0,
+                      known.data_ptr() if known is not None else 0,
                       perm_d.data_ptr() if perm_d is not None else 0, lam_d.data_ptr() if lam_d is not None else 0,
                       self.kd_lambda, B, logits.shape[1], dlogits.data_ptr(), loss_acc.data_ptr(), _stream())
         grads = self.engine._backward(saved, dlogits)
         return loss_acc, grads[None]
 
-    def _graph_fwd_bwd(self, spec, y, teacher, perm_d, lam_d):
-        key = (tuple(spec.shape), tuple(y.shape), teacher is not None, perm_d is not None,
-               tuple(float(getattr(m, "temperature", 0.0)) for m in self.model.modules() if hasattr(m, "temperature")))
+    def _graph_key(self, spec, y, teacher, perm_d, known):
+        """everything a captured graph bakes in: shapes, optional-operand presence and the host scalars passed by value
+        (loss weight, dropout rate, BatchNorm momentum / eps, DynamicConv temperatures)"""
+        bn = next((m for m in self.model.modules() if isinstance(m, torch.nn.BatchNorm2d)), None)
+        return (tuple(spec.shape), tuple(y.shape), teacher is not None, perm_d is not None, known is not None,
+                float(self.kd_lambda), float(self.model.classifier[4].p),
+                (float(bn.momentum), float(bn.eps)) if bn is not None else None,
+                tuple(float(getattr(m, "temperature", 0.0)) for m in self.model.modules() if hasattr(m, "temperature")))
+
+    def _graph_fwd_bwd(self, spec, y, teacher, perm_d, lam_d, known=None):
+        key = self._graph_key(spec, y, teacher, perm_d, known)
         g = self._graphs.get(key)
         if g is None:
-            g = self._capture(spec, y, teacher, perm_d, lam_d)
-            self._graphs = {key: g}             # one live graph (a new shape / temperature replaces it)
+            g = self._capture(spec, y, teacher, perm_d, lam_d, known)
+            self._graphs = {key: g}             # one live graph (a new shape / scalar replaces it)
         g["spec"].copy_(spec.unsqueeze(1), non_blocking=True)
         g["y"].copy_(y, non_blocking=True)
         if teacher is not None:
             g["teacher"].copy_(teacher, non_blocking=True)
+        if known is not None:
+            g["known"].copy_(known, non_blocking=True)
         if perm_d is not None:
             g["perm"].copy_(perm_d, non_blocking=True)
             g["lam"].copy_(lam_d, non_blocking=True)
         g["graph"].replay()
         return g["loss"], g["grads"]
 
-    def _capture(self, spec, y, teacher, perm_d, lam_d):
+    def _capture(self, spec, y, teacher, perm_d, lam_d, known=None):
         dev = spec.device
         st = {"spec": spec.unsqueeze(1).clone(), "y": y.clone(),
               "teacher": teacher.clone() if teacher is not None else None,
+              "known": known.clone() if known is not None else None,
               "perm": perm_d.clone() if perm_d is not None else None,
               "lam": lam_d.clone() if lam_d is not None else None}
         # eager warm-up on a side stream (allocator / one-time attribute calls); BatchNorm buffers are restored
@@ -159,25 +229,27 @@ class AudioSetTrainer:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(2):
-                self._core(st["spec"], st["y"], st["teacher"], st["perm"], st["lam"])
+                self._core(st["spec"], st["y"], st["teacher"], st["perm"], st["lam"], st["known"])
         torch.cuda.current_stream().wait_stream(side)
         with torch.no_grad():
             for b, sb in zip(self.model.buffers(), saved_buffers):
                 b.copy_(sb)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            loss_acc, flat_g = self._core(st["spec"], st["y"], st["teacher"], st["perm"], st["lam"])
+            loss_acc, flat_g = self._core(st["spec"], st["y"], st["teacher"], st["perm"], st["lam"], st["known"])
         st.update(graph=graph, loss=loss_acc, grads=flat_g)
         return st
 
-    def step(self, wave, y, teacher=None, perm=None, lam=None):
+    def step(self, wave, y, teacher=None, perm=None, lam=None, teacher_known=None):
         self.model.train()
         self.mel.train()
-        loss_acc, flat_g = self.forward_backward(wave, y, teacher, perm, lam)
-        if self.world > 1:
-            torch.distributed.all_reduce(flat_g, group=self.pg)        # one collective per step (sum)
-        self.steps += 1
-        lib().adam_step(self.flat_p.data_ptr(), flat_g.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
-                        flat_g.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                        1 if self.adamw else 0, self.steps, 1.0 / self.world, _stream())
+        self.engine.dropout_p = float(self.model.classifier[4].p)     # read at call time, not at engine construction
+        with torch.cuda.device(self.flat_p.device):
+            loss_acc, flat_g = self.forward_backward(wave, y, teacher, perm, lam, teacher_known)
+            if self.world > 1:
+                torch.distributed.all_reduce(flat_g, group=self.pg)        # one collective per step (sum)
+            self.steps += 1
+            lib().adam_step(self.flat_p.data_ptr(), flat_g.data_ptr(), self.exp_avg.data_ptr(),
+                            self.exp_avg_sq.data_ptr(), flat_g.numel(), self.current_lr(), self.betas[0], self.betas[1],
+                            self.eps, self.weight_decay, 1 if self.adamw else 0, self.steps, 1.0 / self.world, _stream())
         return loss_acc

@@ -245,9 +245,11 @@ int eat_mixup(const float* x, const int* perm, const float* lam, float* out, int
               cudaStream_t stream);
 /* Hard-label + knowledge-distillation BCE-with-logits and its gradient, ex_audioset.py:149-189.
  * loss_acc (fp64[2], caller-zeroed) += {kd*label_loss, (1-kd)*distillation_loss}; teacher/perm/lam optional
- * (NULL teacher: plain BCE, weight 1).  dlogits = d(total loss)/d(logits), may be NULL. */
-int eat_bce_kd_loss(const float* logits, const float* y, const float* teacher, const int* perm, const float* lam,
-                    float kd_lambda, int B, int C, float* dlogits, double* loss_acc, cudaStream_t stream);
+ * (NULL teacher: plain BCE, weight 1).  teacher_known [B] (optional, 1/0): 0 zeroes the distillation loss of a clip
+ * without teacher predictions, ex_audioset.py:166-178.  dlogits = d(total loss)/d(logits), may be NULL. */
+int eat_bce_kd_loss(const float* logits, const float* y, const float* teacher, const float* teacher_known,
+                    const int* perm, const float* lam, float kd_lambda, int B, int C, float* dlogits,
+                    double* loss_acc, cudaStream_t stream);
 /* torch.optim.Adam (adamw = 0) / AdamW (adamw = 1) on flat fp32 arenas, ex_audioset.py:86-91,198;
  * grad_scale multiplies the gradient first (1/world_size after a sum all-reduce). step counts from 1. */
 int eat_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,

@@ -73,7 +73,7 @@ def golden_mel():
     print("mel", y.shape, y2.shape, y3.shape, y4.shape)
 
 
-def run_net(tag, factory, width, n_samples, batch, extra_eval=None):
+def run_net(tag, factory, width, n_samples, batch, train=True):
     torch.manual_seed(0)
     model = quiet(factory, width_mult=width)
     synth_state_(model, seed=7)
@@ -95,7 +95,7 @@ def run_net(tag, factory, width, n_samples, batch, extra_eval=None):
     cal_rm, cal_rv = get_bn_stats(model)
     res = {"spec_digest": fmap_digest([spec]), "cal_rm": cal_rm.numpy(), "cal_rv": cal_rv.numpy()}
     import json
-    with open(os.path.join(HERE, f"statedict_{tag}.json"), "w") as fh:      # on-disk checkpoint contract
+    with open(os.path.join(HERE, f"statedict_{tag.split('_')[0]}.json"), "w") as fh:      # on-disk checkpoint contract
         json.dump({k: list(v.shape) for k, v in model.state_dict().items()}, fh, indent=0)
     # ---- eval
     model.eval()
@@ -107,6 +107,10 @@ def run_net(tag, factory, width, n_samples, batch, extra_eval=None):
             logits, feat = model(spec)
             _, fmaps = model._forward_impl(spec, return_fmaps=True)
     res.update(eval_logits=logits.numpy(), eval_feat=feat.numpy(), eval_fmaps=fmap_digest(fmaps))
+    if not train:
+        np.savez_compressed(os.path.join(HERE, f"{tag}.npz"), **res)
+        print(tag, "eval logits absmax", logits.abs().max().item())
+        return
     # ---- train: batch-stat BN, dropout disabled (p=0) so the result is deterministic
     model.train()
     for m in model.modules():
@@ -136,10 +140,63 @@ def run_net(tag, factory, width, n_samples, batch, extra_eval=None):
     print(tag, "eval logits absmax", logits.abs().max().item(), "train loss", loss.item())
 
 
+def state_digest(sd):
+    """per-tensor L2 norm + 4 strided samples of a state_dict (floating tensors only)"""
+    out = {}
+    for k, v in sd.items():
+        if not torch.is_floating_point(v):
+            out[k] = {"int": int(v)}
+            continue
+        f = v.detach().flatten().double()
+        idx = torch.linspace(0, f.numel() - 1, 4).long()
+        out[k] = {"norm": f.norm().item(), "samples": [float(x) for x in f[idx]]}
+    return out
+
+
+def golden_script():
+    """The reference's OWN scripts, unchanged, with the reference's own modules on CPU (scripts/run_reference_script.py
+    --side reference): ex_audioset.py --train (mixup, hard + distillation loss with the unknown-teacher mask, Adam,
+    LambdaLR schedule, validation; ex_audioset.py:120-222) and inference.py on the wav fixture.  The GPU test
+    (tests/test_gpu_refscripts.py) runs the same scripts with `--side ours --cuda` and compares what they log/print."""
+    import json
+    import re
+    import tempfile
+    from tests import refscripts as R
+    os.chdir(REPO)
+    with tempfile.TemporaryDirectory() as wd:
+        env = R.make_workdir(wd, checkpoints=("mn04_as", "mn10_as"))
+        log, ck = os.path.join(wd, "log.json"), os.path.join(wd, "final.pt")
+        r = R.run_script(wd, "reference", "ex_audioset.py", R.SCRIPT_ARGS, env, log_json=log, keep_checkpoint=ck)
+        assert r.returncode == 0, r.stderr[-3000:]
+        sd = torch.load(ck, map_location="cpu")
+        res = {"args": R.SCRIPT_ARGS, "env": R.SCRIPT_ENV, "epochs": R.read_log(log), "final_state": state_digest(sd)}
+        r = R.run_script(wd, "reference", "inference.py", ["--model_name", "mn10_as", "--audio_path",
+                                                          os.path.join(R.ref_root(), "resources", "metro_station-paris.wav")],
+                         env, no_dropout=False)
+        assert r.returncode == 0, r.stderr[-3000:]
+        rows = re.findall(r"^(.+): (\d\.\d{3})$", r.stdout, flags=re.M)
+        assert len(rows) == 10, r.stdout
+        res["inference_top10"] = [[a, float(b)] for a, b in rows]
+    with open(os.path.join(HERE, "script_mn04.json"), "w") as fh:
+        json.dump(res, fh, indent=0)
+    print("script: epochs", [e["train_loss"] for e in res["epochs"]], "top1", res["inference_top10"][0])
+
+
+JOBS = {
+    "mel": golden_mel,
+    "mn10": lambda: run_net("mn10", ref_mn, 1.0, 64000, 2),
+    "mn04": lambda: run_net("mn04", ref_mn, 0.4, 32000, 2),
+    "mn20": lambda: run_net("mn20", ref_mn, 2.0, 32000, 1),
+    "dymn10": lambda: run_net("dymn10", ref_dymn, 1.0, 64000, 2),
+    "dymn04": lambda: run_net("dymn04", ref_dymn, 0.4, 32000, 2),
+    # the shapes the benchmark times (10 s clips -> 1000 frames) and the widths BASELINE.json names (C4: dymn20, C5: mn40)
+    "mn10_10s": lambda: run_net("mn10_10s", ref_mn, 1.0, 320000, 2),
+    "dymn20_10s": lambda: run_net("dymn20_10s", ref_dymn, 2.0, 320000, 2),
+    "dymn20": lambda: run_net("dymn20", ref_dymn, 2.0, 64000, 2),
+    "mn40_10s": lambda: run_net("mn40_10s", ref_mn, 4.0, 320000, 1, train=False),
+    "script": golden_script,
+}
+
 if __name__ == "__main__":
-    golden_mel()
-    run_net("mn10", ref_mn, 1.0, 64000, 2)
-    run_net("mn04", ref_mn, 0.4, 32000, 2)
-    run_net("mn20", ref_mn, 2.0, 32000, 1)
-    run_net("dymn10", ref_dymn, 1.0, 64000, 2)
-    run_net("dymn04", ref_dymn, 0.4, 32000, 2)
+    for name in (sys.argv[1:] or list(JOBS)):
+        JOBS[name]()

@@ -9,7 +9,7 @@ from oracle import net_oracle
 from tests.util import NETS, build_model, fmap_digest, golden, net_inputs, topk_match
 
 pytestmark = pytest.mark.gpu
-MN_TAGS = ["mn10", "mn04", "mn20"]
+MN_TAGS = ["mn10", "mn04", "mn20", "mn10_10s", "mn40_10s"]     # *_10s: the benchmarked 1000-frame shape
 
 
 def _layer_report(tag, model, spec):

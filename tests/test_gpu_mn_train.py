@@ -31,7 +31,7 @@ def _run(tag, precision="fp32", gemm="auto"):
 
 
 @pytest.mark.parametrize("gemm", ["simt", "auto"])
-@pytest.mark.parametrize("tag", ["mn10", "mn04"])
+@pytest.mark.parametrize("tag", ["mn10", "mn04", "mn10_10s"])
 def test_mn_train_step_matches_reference_vectors(tag, gemm):
     g, model, logits, loss = _run(tag, gemm=gemm)
     norm_tol, samp_tol, loss_tol = (5e-3, 2e-2, 1e-5) if gemm == "simt" else (2e-2, 6e-2, 2e-5)

@@ -1,0 +1,213 @@
+"""GPU parity of the training-step kernels that sit inside bench.py's timed region but outside the network:
+spectrogram mixup, hard-label + distillation BCE (with the unknown-teacher mask) and the fused Adam step, each against
+the PyTorch ops the reference's loop calls (ex_audioset.py:143-199: tensor arithmetic, F.binary_cross_entropy_with_logits,
+nn.BCEWithLogitsLoss(reduction="none"), torch.optim.Adam / AdamW, LambdaLR), and of AudioSetTrainer.step as a whole
+against that loop written with autograd around this package's model."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from efficientat_b200._lib import lib
+from efficientat_b200.helpers.utils import exp_warmup_linear_down
+from tests.util import build_model
+
+pytestmark = pytest.mark.gpu
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _reference_loss(y_hat, y, teacher, known, rn, lam, kd_lambda):
+    """the loss of ex_audioset.py:143-189, statement by statement (mixup on; kd_lambda > 0 iff teacher is given)"""
+    bs = y_hat.shape[0]
+    if rn is not None:
+        y_mix = y * lam.reshape(bs, 1) + y[rn] * (1. - lam.reshape(bs, 1))
+        samples_loss = F.binary_cross_entropy_with_logits(y_hat, y_mix, reduction="none")
+    else:
+        samples_loss = F.binary_cross_entropy_with_logits(y_hat, y, reduction="none")
+    label_loss = samples_loss.mean()
+    if teacher is not None and kd_lambda > 0:
+        dl = torch.nn.BCEWithLogitsLoss(reduction="none")
+        if rn is not None:
+            soft = dl(y_hat, teacher).mean(dim=1) * lam.reshape(bs) + dl(y_hat, teacher[rn]).mean(dim=1) * (1. - lam.reshape(bs))
+        else:
+            soft = dl(y_hat, teacher)
+        if known is not None:
+            unknown = ~known
+            soft[unknown] = soft[unknown] * 0
+        soft = soft.mean()
+        label_loss = kd_lambda * label_loss
+        soft = (1 - kd_lambda) * soft
+    else:
+        soft = torch.zeros((), device=y_hat.device)
+    return label_loss + soft, label_loss, soft
+
+
+def test_mixup_kernel_matches_reference_expression():
+    g = torch.Generator().manual_seed(0)
+    B, F_, T = 6, 128, 101                      # per-sample size 12928 (multiple of 4), odd T
+    x = torch.randn(B, 1, F_, T, generator=g).cuda()
+    rn = torch.randperm(B, generator=g)
+    lam = (torch.rand(B, generator=g) * 0.5 + 0.5)
+    want = x * lam.cuda().reshape(B, 1, 1, 1) + x[rn.cuda()] * (1. - lam.cuda().reshape(B, 1, 1, 1))   # ex_audioset.py:145-146
+    out = torch.empty_like(x)
+    lib().mixup(x.data_ptr(), rn.int().cuda().data_ptr(), lam.cuda().data_ptr(), out.data_ptr(), B, F_ * T, _st())
+    assert (out - want).abs().max().item() <= 1e-6
+
+
+@pytest.mark.parametrize("mix", [True, False])
+@pytest.mark.parametrize("with_teacher,with_mask", [(False, False), (True, False), (True, True)])
+def test_bce_kd_loss_and_gradient_match_reference(mix, with_teacher, with_mask):
+    g = torch.Generator().manual_seed(1)
+    B, C, kd = 8, 527, 0.1
+    z = (torch.randn(B, C, generator=g) * 3).cuda().requires_grad_(True)
+    y = (torch.rand(B, C, generator=g) < 0.01).float().cuda()
+    teacher = torch.sigmoid(torch.randn(B, C, generator=g)).cuda() if with_teacher else None
+    known = torch.tensor([True, False, True, True, False, True, True, True]).cuda() if with_mask else None
+    rn = torch.randperm(B, generator=g).cuda() if mix else None
+    lam = (torch.rand(B, generator=g) * 0.5 + 0.5).cuda() if mix else None
+    loss, label, soft = _reference_loss(z, y, teacher, known, rn, lam, kd)
+    loss.backward()
+    dz = torch.empty(B, C, device="cuda")
+    acc = torch.zeros(2, device="cuda", dtype=torch.float64)
+    lib().bce_kd_loss(z.data_ptr(), y.data_ptr(), teacher.data_ptr() if with_teacher else 0,
+                      known.float().data_ptr() if with_mask else 0, rn.int().data_ptr() if mix else 0,
+                      lam.data_ptr() if mix else 0, kd, B, C, dz.data_ptr(), acc.data_ptr(), _st())
+    assert abs(acc[0].item() - label.item()) <= 2e-6 * max(1.0, abs(label.item()))
+    assert abs(acc[1].item() - soft.item()) <= 2e-6 * max(1.0, abs(soft.item()))
+    assert (dz - z.grad).abs().max().item() <= 1e-9 + 1e-5 * z.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("adamw,wd", [(False, 0.0), (False, 1e-2), (True, 1e-2)])
+def test_adam_kernel_matches_torch_optim(adamw, wd):
+    g = torch.Generator().manual_seed(2)
+    n, world = 100003, 4
+    p0 = torch.randn(n, generator=g).cuda()
+    ref_p = p0.clone().requires_grad_(True)
+    opt = (torch.optim.AdamW if adamw else torch.optim.Adam)([ref_p], lr=8e-4, weight_decay=wd)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, exp_warmup_linear_down(3, 4, 2, 0.01))
+    lam = exp_warmup_linear_down(3, 4, 2, 0.01)
+    p, m, v = p0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    step = 0
+    for epoch in range(4):
+        for _ in range(2):
+            grad_sum = (torch.randn(n, generator=g) * 10 ** float(torch.randint(-6, 1, (1,), generator=g))).cuda()
+            ref_p.grad = grad_sum / world                       # DDP hands the optimiser the mean over ranks
+            opt.step()
+            step += 1
+            lib().adam_step(p.data_ptr(), grad_sum.data_ptr(), m.data_ptr(), v.data_ptr(), n, 8e-4 * lam(epoch), 0.9, 0.999,
+                            1e-8, wd, 1 if adamw else 0, step, 1.0 / world, _st())
+        sched.step()
+        assert abs(sched.get_last_lr()[0] - 8e-4 * lam(epoch + 1)) < 1e-12
+    err = (p - ref_p.detach()).abs().max().item()
+    assert err <= 2e-6, err                                     # 8 steps of <= 8e-4 each; fp32 rounding of the update
+
+
+def _mk_trainer(graph, kd=0.1, schedule=None, tag="mn04"):
+    from efficientat_b200.models.preprocess import AugmentMelSTFT
+    from efficientat_b200.train import AudioSetTrainer
+    model = build_model(tag).cuda()
+    with contextlib.redirect_stdout(io.StringIO()):
+        mel = AugmentMelSTFT(freqm=0, timem=0).cuda()
+    model.classifier[4].p = 0.0
+    return model, mel, AudioSetTrainer(model, mel, lr=4e-4, kd_lambda=kd, mixup_alpha=0.3, cuda_graph=graph, schedule=schedule)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_trainer_step_matches_reference_loop_with_autograd(graph):
+    """Three steps of AudioSetTrainer.step (device kernels: mixup, loss + mask, hand-chained backward, fused Adam,
+    epoch-wise learning rate) against the reference's loop body written with torch ops + autograd + torch.optim.Adam +
+    LambdaLR around the SAME model class (whose forward/backward are pinned to the reference elsewhere).  Same mel
+    jitter draws, same mixup draws.  Losses must agree to 2e-6; parameter updates of every tensor whose gradient is not
+    analytically zero to 2 % of the update's norm (Adam's first steps move a parameter by +-lr whatever the size of
+    its gradient, so a tensor whose true gradient is 0 -- a BatchNorm bias feeding a 1x1 conv + training-mode
+    BatchNorm -- performs a random walk of fp32 summation noise in both implementations; those are skipped by
+    their gradient norm, < 1e-6 of the largest)."""
+    from efficientat_b200.synth import synth_labels, synth_waveform
+    B = 4
+    sched = exp_warmup_linear_down(2, 4, 1, 0.1)
+    wave = synth_waveform(B, 32000, seed=3).cuda()
+    y = synth_labels(B, 527, seed=4, p=0.02).cuda()
+    teacher = torch.sigmoid(torch.randn(B, 527, generator=torch.Generator().manual_seed(5))).cuda()
+    known = torch.tensor([True, True, False, True]).cuda()
+    draws = [(torch.randperm(B, generator=torch.Generator().manual_seed(10 + i)),
+              torch.rand(B, generator=torch.Generator().manual_seed(20 + i)) * 0.5 + 0.5) for i in range(3)]
+
+    # ---- reference loop (autograd around this package's modules)
+    model, mel, _ = _mk_trainer(False)
+    model.train(); mel.train()
+    p_before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    opt = torch.optim.Adam(model.parameters(), lr=4e-4)
+    lr_sched = torch.optim.lr_scheduler.LambdaLR(opt, sched)
+    ref_losses, gnorm = [], {}
+    torch.manual_seed(77)
+    for i, (rn, lam) in enumerate(draws):
+        x = mel(wave).unsqueeze(1)
+        lam_d, rn_d = lam.cuda(), rn.cuda()
+        x = x * lam_d.reshape(B, 1, 1, 1) + x[rn_d] * (1. - lam_d.reshape(B, 1, 1, 1))
+        y_hat, _ = model(x)
+        loss, label, soft = _reference_loss(y_hat, y, teacher, known, rn_d, lam_d, 0.1)
+        loss.backward()
+        if i == 0:
+            gnorm = {n: p.grad.norm().item() for n, p in model.named_parameters()}
+        opt.step()
+        opt.zero_grad()
+        lr_sched.step()                                         # one "epoch" per step: exercises the schedule
+        ref_losses.append((label.item(), soft.item()))
+    ref_delta = {n: (p.detach() - p_before[n]) for n, p in model.named_parameters()}
+
+    # ---- trainer
+    model2, mel2, tr = _mk_trainer(graph, schedule=sched)
+    torch.manual_seed(77)
+    losses = []
+    for i, (rn, lam) in enumerate(draws):
+        tr.set_epoch(i)
+        acc = tr.step(wave, y, teacher, perm=rn, lam=lam, teacher_known=known)
+        losses.append(acc.cpu().tolist())
+    for (a, b), (ra, rb) in zip(losses, ref_losses):
+        assert abs(a - ra) <= 2e-6 and abs(b - rb) <= 2e-6, (losses, ref_losses)
+    gmax = max(gnorm.values())
+    worst, skipped = 0.0, 0
+    for n, p in model2.named_parameters():
+        if gnorm[n] < 1e-6 * gmax:
+            skipped += 1
+            continue
+        d = p.detach() - p_before[n]
+        rel = (d - ref_delta[n]).norm().item() / max(ref_delta[n].norm().item(), 1e-12)
+        worst = max(worst, rel)
+        assert rel <= 2e-2, (n, rel, gnorm[n])
+    print(f"[parity] trainer (graph={graph}) vs autograd loop: worst update rel err {worst:.2e}, {skipped} zero-gradient tensors skipped")
+    assert skipped < 40
+
+
+def test_trainer_rejects_bad_inputs():
+    model, mel, tr = _mk_trainer(False)
+    from efficientat_b200.synth import synth_labels, synth_waveform
+    wave = synth_waveform(2, 32000, seed=3).cuda()
+    y = synth_labels(2, 527, seed=4).cuda()
+    with pytest.raises(ValueError):
+        tr.step(wave, y[:1])
+    with pytest.raises(RuntimeError):
+        tr.step(wave, y.cpu())
+    acc = tr.step(wave, y.double())                              # converted, not reinterpreted
+    assert np.isfinite(acc.cpu().numpy()).all()
+    with pytest.raises(AssertionError):
+        from efficientat_b200.train import AudioSetTrainer
+        AudioSetTrainer(model, mel, kd_lambda=1.5)
+
+
+def test_engine_rejects_misplaced_or_half_parameters():
+    model = build_model("mn04").cuda().eval()
+    x = torch.zeros(1, 1, 128, 100, device="cuda")
+    model(x)
+    model.features[3].block[0][0].weight.data = model.features[3].block[0][0].weight.data.cpu()
+    with pytest.raises(RuntimeError, match="features.3.block.0.0.weight"):
+        model(x)
+    model = build_model("mn04").cuda().half().eval()
+    with pytest.raises(RuntimeError, match="fp32"):
+        model(x)

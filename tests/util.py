@@ -10,7 +10,10 @@ from efficientat_b200.synth import set_bn_stats, synth_labels, synth_state_, syn
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 NETS = {"mn10": ("mn", 1.0, 64000, 2), "mn04": ("mn", 0.4, 32000, 2), "mn20": ("mn", 2.0, 32000, 1),
-        "dymn10": ("dymn", 1.0, 64000, 2), "dymn04": ("dymn", 0.4, 32000, 2)}
+        "dymn10": ("dymn", 1.0, 64000, 2), "dymn04": ("dymn", 0.4, 32000, 2),
+        # the benchmarked shape (10 s clips = 1000 frames) and the widths BASELINE.json's configs C4 / C5 name
+        "mn10_10s": ("mn", 1.0, 320000, 2), "dymn20_10s": ("dymn", 2.0, 320000, 2), "dymn20": ("dymn", 2.0, 64000, 2),
+        "mn40_10s": ("mn", 4.0, 320000, 1)}
 
 
 def golden(name):
