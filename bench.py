@@ -32,7 +32,11 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"],
+                    help="ours: this package; reference: the reference's CPU PyTorch path on the host cores; "
+                         "reference-gpu: the reference's own modules (cuFFT/cuDNN/cuBLAS) on the same GPUs")
+    ap.add_argument("--amp", default="none", choices=["none", "bf16"], help="reference-gpu only: torch.autocast dtype")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the gpu_baseline leg of the default run")
     ap.add_argument("--batch", type=int, default=256, help="clips per GPU per step")
     ap.add_argument("--precision", default=os.environ.get("EAT_PRECISION", "fp32"), choices=["fp32", "bf16"])
     ap.add_argument("--model", default="mn10", choices=["mn04", "mn10", "mn20", "mn40", "dymn04", "dymn10", "dymn20"])
@@ -84,30 +88,57 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_step_factory(batch, width=1.0):
-    """The reference algorithm (oracle port: plain PyTorch ops, fp32) for one training step on the host."""
+def _synth_batch(batch, seed):
+    """the synthetic shard both arms train on: waveforms, labels, teacher soft targets, unknown-teacher mask"""
+    from efficientat_b200.synth import synth_labels, synth_waveform
+    wave = synth_waveform(batch, CLIP_SAMPLES, seed=1000 + seed)
+    y = synth_labels(batch, N_CLASSES, seed=2000 + seed)
+    teacher = torch.sigmoid(torch.randn(batch, N_CLASSES, generator=torch.Generator().manual_seed(3000 + seed)))
+    known = torch.ones(batch, dtype=torch.bool)
+    known[4::5] = False                                       # every 5th clip has no teacher entry (ex_audioset.py:166-177)
+    return wave, y, teacher, known
+
+
+def cpu_reference_step_factory(batch, model="mn10"):
+    """One training step of the reference on the host: the reference's OWN modules from the baseline/_ref mirror when it
+    is present (kind "reference"), else the oracle port of the same algorithm (kind "port").  Same step as the GPU arm:
+    mel + mixup + forward + hard/distillation BCE with the unknown-teacher mask + backward + Adam."""
+    from baseline import ref_step
+    wave, y, teacher, known = _synth_batch(batch, 0)
+    dev = torch.device("cpu")
+    if ref_step.available():
+        return ref_step.make_train_step(model, wave, y, teacher, known, dev), "reference"
     from oracle import mel_oracle, net_oracle
+    from efficientat_b200.helpers.utils import mixup
     from efficientat_b200.models.mn.model import get_model
-    from efficientat_b200.synth import synth_labels, synth_state_, synth_waveform
+    from efficientat_b200.synth import synth_state_
+    if model.startswith("dymn"):
+        from efficientat_b200.models.dymn.model import get_model
+    width = ref_step.WIDTH[model]
     torch.manual_seed(0)
-    model = synth_state_(get_model(width_mult=width, verbose=False), seed=7)
-    sd = {k: v.clone() for k, v in model.state_dict().items()}
-    names = [k for k, _ in model.named_parameters()]
+    net = synth_state_(get_model(width_mult=width, verbose=False), seed=7)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    names = [k for k, _ in net.named_parameters()]
     for k in names:
         sd[k].requires_grad_(True)
     opt = torch.optim.Adam([sd[k] for k in names], lr=8e-4)
-    wave = synth_waveform(batch, CLIP_SAMPLES, seed=1)
-    y = synth_labels(batch, N_CLASSES, seed=2)
+    fwd = net_oracle.dymn_forward if model.startswith("dymn") else net_oracle.mn_forward
+    kd = 0.1
 
     def step():
         spec = mel_oracle.mel_forward(wave).unsqueeze(1)
-        logits, _ = net_oracle.mn_forward(sd, spec, width_mult=width, training=True)
-        loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, y)
+        rn, lam = mixup(batch, 0.3)
+        spec = spec * lam.reshape(batch, 1, 1, 1) + spec[rn] * (1. - lam.reshape(batch, 1, 1, 1))
+        logits, _ = fwd(sd, spec, width_mult=width, training=True, **({"temperature": 30.0} if model.startswith("dymn") else {}))
+        bce = torch.nn.functional.binary_cross_entropy_with_logits
+        y_mix = y * lam.reshape(batch, 1) + y[rn] * (1. - lam.reshape(batch, 1))
+        soft = bce(logits, teacher, reduction="none").mean(1) * lam + bce(logits, teacher[rn], reduction="none").mean(1) * (1. - lam)
+        loss = kd * bce(logits, y_mix) + (1 - kd) * (soft * known.float()).mean()
         opt.zero_grad()
         loss.backward()
         opt.step()
         return float(loss.detach())
-    return step
+    return step, "port"
 
 
 def usable_cores():
@@ -131,11 +162,11 @@ def usable_cores():
     return n
 
 
-def time_cpu_reference(batch, steps, warmup, budget_s=150.0):
-    """-> (clips/s, s/step, threads, clips per step).  The per-step sample is bounded: a one-clip calibration step
+def time_cpu_reference(batch, steps, warmup, budget_s=150.0, model="mn10"):
+    """-> (clips/s, s/step, threads, clips per step, kind).  The per-step sample is bounded: a two-clip calibration step
     (which is also a warm-up) sets the clips per step so that warm-up + timed steps stay within `budget_s`."""
     cores = usable_cores()
-    one = cpu_reference_step_factory(1)
+    one, kind = cpu_reference_step_factory(2, model)          # 2 clips: training-mode BatchNorm needs > 1 value per channel
     best = None
     for n in ([cores, 16] if cores > 16 else [cores]):      # a shared box may expose more CPUs than it lets us run on:
         torch.set_num_threads(n)                            # keep whichever thread count is actually faster
@@ -145,35 +176,124 @@ def time_cpu_reference(batch, steps, warmup, budget_s=150.0):
         dt1 = time.perf_counter() - t0
         if best is None or dt1 < best[0]:
             best = (dt1, n)
-    t1, cores = best                                        # seconds per clip, threads used
+    t1, cores = best[0] / 2, best[1]                        # seconds per clip, threads used
     torch.set_num_threads(cores)
-    batch = max(1, min(batch, int(budget_s / max(t1 * (steps + max(1, warmup)), 1e-6))))
-    step = cpu_reference_step_factory(batch)
+    batch = max(2, min(batch, int(budget_s / max(t1 * (steps + max(1, warmup)), 1e-6))))
+    step, kind = cpu_reference_step_factory(batch, model)
     for _ in range(max(1, warmup)):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps, cores, batch
+    return batch * steps / dt, dt / steps, cores, batch, kind
+
+
+def _workload(args, where):
+    return (f"{args.model}_as training step: mel + mixup + fwd + BCE/KD loss (unknown-teacher mask) + bwd + Adam "
+            f"(ex_audioset.py:135-199), 10 s @ 32 kHz clips, {where}")
 
 
 def run_reference_arm(args):
+    """`--impl reference`: the reference's CPU PyTorch implementation of the same step on the host cores (rank 0 only).
+    Exactly --steps timed and --warmup untimed steps; each step is a bounded sample (clips per step calibrated so the
+    whole run stays within ~2.5 minutes)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    k = min(args.steps, 5)
-    w = min(args.warmup, 1)
-    value, s_per_step, cores, b = time_cpu_reference(args.cpu_baseline_batch, k, w)
-    sample = f"{k} steps x {b} clips (mel+fwd+bwd+Adam, fp32, oracle port of the reference modules)"
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": args.gpus,
-            "steps": k, "warmup": w, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "mn10_as training step (mel+fwd+bwd+Adam) on host cores", "model": args.model,
-                       "batch_per_step": b},
-            "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+    value, s_per_step, cores, b, kind = time_cpu_reference(args.cpu_baseline_batch, args.steps, args.warmup, model=args.model)
+    what = "the reference's own modules (baseline/_ref mirror)" if kind == "reference" else "oracle port of the reference modules"
+    sample = f"{args.steps} steps x {b} clips ({args.warmup} warm-up), same training step as the GPU arm, fp32, {what}"
+    line = {"impl": "reference", "metric": METRIC if args.model == "mn10" else f"clips/sec (10s@32kHz) {args.model}_as fwd+bwd",
+            "value": value, "unit": "clips/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": _workload(args, f"host cores, {b} clips per step (bounded sample of the batch-{args.batch} workload)"),
+                       "model": f"{args.model}_as", "batch_per_step": b},
+            "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def time_reference_gpu(model, mode, B, steps, warmup, dev, amp, world, seed):
+    """the reference's own modules on this GPU (baseline/ref_step.py) -> (ms total over `steps`, peak GiB) or raises"""
+    from baseline import ref_step
+    torch.backends.cudnn.benchmark = True
+    wave, y, teacher, known = (t.to(dev) for t in _synth_batch(B, seed))
+    dt = {"none": None, "bf16": torch.bfloat16}[amp]
+    if mode == "eval":
+        step = ref_step.make_eval_step(model, wave, dev, amp=dt)
+    else:
+        step = ref_step.make_train_step(model, wave, y, teacher, known, dev, amp=dt, ddp=world > 1)
+    torch.cuda.reset_peak_memory_stats(dev)
+    for _ in range(max(warmup, 3)):
+        step()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, torch.cuda.max_memory_allocated(dev) / 2 ** 30
+
+
+def gpu_baseline_entry(model, mode, B, steps, warmup, dev, amp, world, seed):
+    from baseline import ref_step
+    if not ref_step.available():
+        return {"unavailable": "baseline/_ref (mirror of the reference checkout, made by baseline/make_ref.py) is not present"}
+    try:
+        ms, gib = time_reference_gpu(model, mode, B, steps, warmup, dev, amp, world, seed)
+    except torch.cuda.OutOfMemoryError:
+        torch.cuda.empty_cache()
+        return {"unavailable": f"reference modules ran out of memory at batch {B}/GPU", "amp": amp}
+    return {"value": world * B * steps / (ms * 1e-3), "unit": "clips/s", "ms_per_step": ms / steps, "steps": steps,
+            "amp": amp, "batch_per_gpu": B, "peak_mem_gib": round(gib, 1),
+            "what": "the reference's own nn.Modules (baseline/_ref mirror) through stock PyTorch: cuFFT + cuDNN + cuBLAS, "
+                    "cudnn.benchmark, " + ("fp32 params / TF32 convolutions (PyTorch defaults)" if amp == "none" else "torch.autocast(bfloat16)")
+                    + (", DistributedDataParallel" if world > 1 else "") + "; same synthetic batch and loop body "
+                    "(ex_audioset.py:135-199 incl. its 3 loss read-backs per step)"}
+
+
+def run_reference_gpu_arm(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl reference-gpu needs a CUDA device")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    with ClockSampler(local) as clocks:
+        r = gpu_baseline_entry(args.model, args.mode, args.batch, args.steps, args.warmup, dev, args.amp, world, rank)
+    if rank == 0:
+        if "unavailable" in r:
+            print(json.dumps({"impl": "reference-gpu", **r}), flush=True)
+        else:
+            line = {"impl": "reference-gpu", "metric": METRIC if (args.mode == "train" and args.model == "mn10") else
+                    f"clips/sec (10s@32kHz) {args.model}_as {'fwd+bwd' if args.mode == 'train' else 'fwd'}",
+                    "value": r["value"], "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                    "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                    "dtype": "f32" if args.amp == "none" else "bf16", "data": "synthetic",
+                    "config": {"workload": _workload(args, f"batch {args.batch}/GPU") if args.mode == "train" else
+                               f"{args.model}_as mel + eval forward, batch {args.batch}/GPU", "model": f"{args.model}_as",
+                               "global_batch": args.batch * world, "parallelism": f"ddp{world}", "amp": args.amp},
+                    "gpu_baseline": r, "clocks": clocks.summary()}
+            print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
@@ -184,7 +304,17 @@ def algo_bytes(name, a):
         A, adt, W, wt, C, cdt, M, N, K = a[:9]
         res = a[17]
         return M * K * sz(adt) + M * N * sz(cdt) * (2 if res else 1) + N * K * 4
-    if name == "eat_gemm_simt_wgrad":
+    if name == "eat_pw_tc_dyn_fwd":          # + the dyn_k weight banks (read once; re-reads per tile hit L2)
+        A, dt, W, att, nk, C, M, N, K, rps = a[:10]
+        res = a[16]
+        return M * K * sz(dt) + M * N * sz(dt) * (2 if res else 1) + nk * N * K * 4
+    if name == "eat_pw_tc_wgrad_persample":  # G + A read once, per-sample gradients written once
+        G, A, dt, S, M, N, K, rps = a[:8]
+        return M * (N + K) * sz(dt) + (M // rps) * N * K * 4
+    if name == "eat_dyn_wgrad_mix":          # S [B, n] read once, banks read + bank gradients written
+        S, att, W, dW, datt, B, n, k = a[:8]
+        return B * n * 4 + 2 * k * n * 4
+    if name == "eat_gemm_simt_wgrad" or name == "eat_pw_tc_wgrad":
         G, gdt, A, adt, dW, db, M, N, K = a[:9]
         return M * N * sz(gdt) + M * K * sz(adt) + N * K * 4
     if name == "eat_dw_conv_fwd":
@@ -304,7 +434,7 @@ def run_ours(args):
         mel.eval()
 
         class _Eval:                                             # same .step() shape as the trainer
-            def step(self, w, y_, t_):
+            def step(self, w, y_, t_, k_=None):
                 with torch.no_grad():
                     logits, _ = model(mel(w).unsqueeze(1))
                 return logits[:, :2].double().sum(0)             # tiny device result read back in the e2e loop
@@ -314,10 +444,19 @@ def run_ours(args):
     torch.manual_seed(100 + rank)
 
     # synthetic shard for this rank: waveforms, labels, teacher soft targets (sigmoid of N(0,1) logits)
-    wave_h = synth_waveform(B, CLIP_SAMPLES, seed=1000 + rank).pin_memory()
-    y_h = synth_labels(B, N_CLASSES, seed=2000 + rank).pin_memory()
-    t_h = torch.sigmoid(torch.randn(B, N_CLASSES, generator=torch.Generator().manual_seed(3000 + rank))).pin_memory()
-    wave, y, teacher = wave_h.to(dev), y_h.to(dev), t_h.to(dev)
+    wave_h, y_h, t_h, k_h = _synth_batch(B, rank)
+    wave_h, y_h, t_h, k_h = wave_h.pin_memory(), y_h.pin_memory(), t_h.pin_memory(), k_h.float().pin_memory()
+    wave, y, teacher, known = wave_h.to(dev), y_h.to(dev), t_h.to(dev), k_h.to(dev)
+    if args.mode == "train":
+        real = trainer
+
+        class _Train:                                            # fixed (wave, y, teacher[, known]) signature for the loops below
+            cuda_graph = real.cuda_graph
+
+            def step(self, w, y_, t_, k_=None):
+                real.cuda_graph = self.cuda_graph
+                return real.step(w, y_, t_, teacher_known=known if k_ is None else k_)
+        trainer = _Train()
 
     def barrier():
         if world > 1:
@@ -369,6 +508,9 @@ def run_ours(args):
         trainer.cuda_graph = False
     with KernelTimer(L, only={top}) as kt2:
         for _ in range(args.steps):
+            # park the stream behind a ~60 ms spin kernel so that the host enqueues the whole step ahead of the GPU: the
+            # events then sit directly before / after each launch on the device, with no host gap inside an interval
+            torch.cuda._sleep(int(0.06 * 1.9e9))
             trainer.step(wave, y, teacher)
         torch.cuda.synchronize()
     if use_graph:
@@ -384,12 +526,12 @@ def run_ours(args):
     t0 = time.perf_counter()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    pf.submit(0, (wave_h, y_h, t_h))
+    pf.submit(0, (wave_h, y_h, t_h, k_h))
     for i in range(args.steps):
         if i + 1 < args.steps:
-            pf.submit((i + 1) % 2, (wave_h, y_h, t_h))
-        w_d, y_d, t_d = pf.get(i % 2)
-        loss = trainer.step(w_d, y_d, t_d)
+            pf.submit((i + 1) % 2, (wave_h, y_h, t_h, k_h))
+        w_d, y_d, t_d, k_d = pf.get(i % 2)
+        loss = trainer.step(w_d, y_d, t_d, k_d)
         pf.release(i % 2)
         loss_host = loss.cpu()                      # device -> host read of the step's result (synchronises)
     e3.record()
@@ -400,7 +542,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item())
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
-    h2d = wave_h.numel() * 4 + y_h.numel() * 4 + t_h.numel() * 4
+    h2d = wave_h.numel() * 4 + y_h.numel() * 4 + t_h.numel() * 4 + k_h.numel() * 4
     d2h = loss_host.numel() * 8
 
     if rank == 0:
@@ -447,10 +589,26 @@ def run_ours(args):
             "loss": [float(v) for v in loss_host.tolist()],
         }
         if not args.no_cpu_baseline and world == 1:
-            v, s_per_step, cores, cb = time_cpu_reference(args.cpu_baseline_batch, 2, 1, budget_s=45.0)
-            line["cpu_baseline"] = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
-                                    "sample": f"2 steps x {cb} clips, same training step, fp32, "
-                                              "oracle port of the reference modules on the host cores"}
+            v, s_per_step, cores, cb, kind = time_cpu_reference(args.cpu_baseline_batch, 2, 1, budget_s=30.0, model=args.model)
+            line["cpu_baseline"] = {"value": v, "unit": "clips/s", "cores": cores, "kind": kind,
+                                    "sample": f"2 steps x {cb} clips (1 warm-up), same training step (mixup, hard + "
+                                              "distillation loss with the unknown-teacher mask, Adam), fp32, "
+                                              + ("the reference's own modules (baseline/_ref mirror)" if kind == "reference"
+                                                 else "oracle port of the reference modules") + " on the host cores"}
+    # ---- the reference's own GPU path on the same device(s): cuFFT / cuDNN / cuBLAS through the unmodified modules
+    gb = None
+    if not args.no_gpu_baseline:
+        del trainer, pf
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        gb = {}
+        for amp in ("none", "bf16"):
+            gb["fp32" if amp == "none" else "autocast_bf16"] = gpu_baseline_entry(
+                args.model, args.mode, B, min(args.steps, 5), 3, dev, amp, world, rank)
+    if rank == 0:
+        if gb is not None:
+            line["gpu_baseline"] = gb
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -461,5 +619,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference_arm(a)
+    elif a.impl == "reference-gpu":
+        run_reference_gpu_arm(a)
     else:
         run_ours(a)

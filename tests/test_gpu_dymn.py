@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import net_oracle
-from tests.util import NETS, build_model, fmap_digest, golden, net_inputs, topk_match
+from tests.util import report, NETS, build_model, fmap_digest, golden, net_inputs, topk_match
 
 pytestmark = pytest.mark.gpu
 
@@ -31,7 +31,7 @@ def test_dymn_eval_fp32_matches_reference_vectors(tag, gemm):
         logits, feat = model(spec.cuda())
     logits, feat = logits.cpu().numpy(), feat.cpu().numpy()
     err = np.abs(logits - g["eval_logits"]).max()
-    print(f"[parity] {tag} gemm={gemm}: logit max-abs err {err:.3e}")
+    report(f"[parity] {tag} gemm={gemm}: logit max-abs err {err:.3e}")
     if not err < 1e-3:
         pytest.fail(f"logit max-abs err {err}\n" + _layer_report(tag, model, spec))
     assert np.abs(feat - g["eval_feat"]).max() < 2e-3
@@ -75,15 +75,6 @@ def test_dymn_replace_se_variant_and_bf16():
     with torch.no_grad():
         lb, _ = mb(net_inputs("dymn10")[0].cuda())
     assert np.abs(lb.cpu().numpy() - golden("dymn10")["eval_logits"]).max() < 8e-2
-
-
-def _report(line):
-    import os
-    path = os.environ.get("EAT_TEST_REPORT")
-    print(line)
-    if path:
-        with open(path, "a") as f:
-            f.write(line + "\n")
 
 
 @pytest.mark.parametrize("gemm", ["simt", "auto"])
@@ -144,7 +135,7 @@ def test_dymn_train_step_matches_reference_vectors(tag, gemm):
                 np.abs(samp - g["grad_samples"][i]).max() <= 0.3 * max(gr.abs().max().item(), 1e-7) + atol
             if not wide:
                 very_bad.append(bad[-1])
-    _report(f"[parity] {tag} train gemm={gemm}: logits {lerr:.2e}, worst grad-norm rel err {worst['other']:.2e} "
+    report(f"[parity] {tag} train gemm={gemm}: logits {lerr:.2e}, worst grad-norm rel err {worst['other']:.2e} "
             f"(attention-logit layers {worst['res']:.2e}), {len(bad)} of {len(names)} tensors outside the band")
     assert not very_bad, f"{len(very_bad)} of {len(names)} tensors\n" + "\n".join(very_bad[:60])
     assert len(bad) <= (0 if exact else 2), f"{len(bad)} of {len(names)} tensors\n" + "\n".join(bad[:60])

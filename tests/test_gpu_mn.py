@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import net_oracle
-from tests.util import NETS, build_model, fmap_digest, golden, net_inputs, topk_match
+from tests.util import report, NETS, build_model, fmap_digest, golden, net_inputs, topk_match
 
 pytestmark = pytest.mark.gpu
 MN_TAGS = ["mn10", "mn04", "mn20", "mn10_10s", "mn40_10s"]     # *_10s: the benchmarked 1000-frame shape
@@ -38,7 +38,7 @@ def test_mn_eval_fp32_matches_reference_vectors(tag, gemm):
         logits, feat = model(spec.cuda())
     logits, feat = logits.cpu().numpy(), feat.cpu().numpy()
     err = np.abs(logits - g["eval_logits"]).max()
-    print(f"[parity] {tag} gemm={gemm}: logit max-abs err {err:.3e}")
+    report(f"[parity] {tag} gemm={gemm}: logit max-abs err {err:.3e}")
     if not err < 1e-3:
         pytest.fail(f"logit max-abs err {err}\n" + _layer_report(tag, model, spec))
     assert np.abs(feat - g["eval_feat"]).max() < 1e-3

@@ -15,7 +15,7 @@ import pytest
 import torch
 
 from tests import refscripts as R
-from tests.util import GOLDEN
+from tests.util import report, GOLDEN
 
 pytestmark = pytest.mark.gpu
 
@@ -43,15 +43,15 @@ def test_ex_audioset_train_runs_unchanged_and_matches_reference_run(tmp_path):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     epochs = R.read_log(log)
     assert len(epochs) == len(g["epochs"]) == 3
-    report = []
+    rep = []
     for e, (got, want) in enumerate(zip(epochs, g["epochs"])):
-        report.append({k: (got[k], want[k]) for k in want})
+        rep.append({k: (got[k], want[k]) for k in want})
         for k in ("train_loss", "label_loss", "distillation_loss"):
             assert abs(got[k] - want[k]) <= 2e-4, (e, k, got[k], want[k])
         assert abs(got["learning_rate"] - want["learning_rate"]) <= 1e-12
         assert abs(got["val_loss"] - want["val_loss"]) <= 2e-3, (e, got["val_loss"], want["val_loss"])
         assert abs(got["mAP"] - want["mAP"]) <= 2e-3 and abs(got["ROC"] - want["ROC"]) <= 5e-3
-    print("[parity] ex_audioset.py epochs (ours, reference):", json.dumps(report))
+    report("[parity] ex_audioset.py epochs (ours, reference): " + json.dumps(rep))
     # the checkpoint the script saved: reference key set, every tensor close to the reference run's.  Tensors whose
     # gradient is analytically zero (BatchNorm biases feeding a 1x1 conv + training-mode BatchNorm) random-walk by
     # +-lr per Adam step in either implementation -> 5 % band on their norm; everything else 2e-3.
@@ -68,7 +68,7 @@ def test_ex_audioset_train_runs_unchanged_and_matches_reference_run(tmp_path):
         assert rel <= tol, (k, n, want["norm"])
         if rel > worst[0] and tol < 1e-2:
             worst = (rel, k)
-    print(f"[parity] ex_audioset.py final checkpoint: worst tensor-norm rel err {worst[0]:.2e} ({worst[1]})")
+    report(f"[parity] ex_audioset.py final checkpoint: worst tensor-norm rel err {worst[0]:.2e} ({worst[1]})")
 
 
 @needs_ref
@@ -87,7 +87,7 @@ def test_inference_py_runs_unchanged_and_prints_reference_labels(tmp_path):
     rows = re.findall(r"^(.+): (\d\.\d{3})$", r.stdout, flags=re.M)
     assert len(rows) == 10, r.stdout
     want = g["inference_top10"]
-    print("[parity] inference.py top-10 (ours):", rows)
+    report(f"[parity] inference.py top-10 (ours): {rows}")
     ref_prob = dict((a, b) for a, b in want)
     for r, ((lab, prob), (wlab, wprob)) in enumerate(zip(rows, want)):
         assert abs(float(prob) - wprob) <= 2e-3, (r, lab, prob, wlab, wprob)        # the r-th largest probability

@@ -16,6 +16,15 @@ NETS = {"mn10": ("mn", 1.0, 64000, 2), "mn04": ("mn", 0.4, 32000, 2), "mn20": ("
         "mn40_10s": ("mn", 4.0, 320000, 1)}
 
 
+def report(line):
+    """parity figures the tests measure: printed, and appended to $EAT_TEST_REPORT when set (profiles/*_parity_report.txt)"""
+    print(line)
+    path = os.environ.get("EAT_TEST_REPORT")
+    if path:
+        with open(path, "a") as f:
+            f.write(line + "\n")
+
+
 def golden(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
 
