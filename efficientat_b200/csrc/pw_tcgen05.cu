@@ -21,6 +21,7 @@
 // The kernel is HBM-bound for mn10 widths (arithmetic intensity below the ridge); algorithmic bytes per
 // launch = M*K*sizeof(A) + M*N*sizeof(C) (+ residual) + N*K*4.
 #include <cstdlib>
+#include <cstring>
 
 #include "tc_common.cuh"
 
@@ -640,6 +641,12 @@ extern "C" int eat_pw_tc_fwd(const void* A, int a_dtype, const float* W, int w_t
   if (K % 8 != 0 || N % 8 != 0) { eat_set_error("pw_tc: K and N must be multiples of 8"); return EAT_ERR_ARG; }
   if (M >= (1ll << 31) - BM) { eat_set_error("pw_tc: M too large"); return EAT_ERR_ARG; }
   if ((((uintptr_t)A) | ((uintptr_t)W) | ((uintptr_t)C) | ((uintptr_t)in_scale) | ((uintptr_t)in_shift)) & 15) { eat_set_error("pw_tc: operands must be 16-byte aligned"); return EAT_ERR_ARG; }
+  if (a_dtype == EAT_F32 && !(residual != nullptr && act != EAT_ACT_NONE)) {
+    static const bool use_tma = [] { const char* e = getenv("EAT_PW_IMPL"); return e == nullptr || strcmp(e, "tc") != 0; }();
+    if (use_tma)     // fp32 storage: the TMA-fed TF32x3 kernel (pw_tma.cu)
+      return eat_pw_tma_fwd((const float*)A, W, (float*)C, M, N, K, in_scale, in_shift, in_act, gate, rows_per_sample, scale,
+                            shift, act, (const float*)residual, stat_sum, stat_sq, st);
+  }
   TcParams p;
   p.A = A; p.W = W; p.C = C; p.residual = residual; p.M = (int)M; p.N = N; p.K = K;
   p.xf = InXform{in_scale, in_shift, gate, in_act, rows_per_sample > 0 ? rows_per_sample : 1};

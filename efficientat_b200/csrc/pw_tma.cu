@@ -1,0 +1,704 @@
+// Pointwise (1x1) convolution / Linear for fp32 activations as a TMA-fed tcgen05 GEMM (sm_100a):
+//     C[M,N] = epi( xf(A)[M,K] . W[N,K]^T  (+ R[M,N]) )          A, C, R: NHWC activation rows, fp32; W: fp32
+// Same contract and reference call sites as pw_tcgen05.cu (models/mn/block_types.py:140-147,167-171;
+// models/mn/model.py:160-166; every data-gradient GEMM of loss.backward(), ex_audioset.py:197).
+//
+// Why a second kernel: in pw_tcgen05.cu eight producer warps carry every operand byte global -> registers -> smem;
+// their scalar tile walk and register-limited loads (not bytes, not MMAs) set a ~2000-cycle floor per 128-row tile
+// (profiles/r01_pw_tc_role_timing.txt).  Here no thread touches global memory on the operand path:
+//
+//   warp 0   TMA producer : ONE thread.  cp.async.bulk.tensor (2-D tiled, SWIZZLE_128B) lands raw fp32 tiles of A
+//                           [128 rows x 32 k] (and of W, and of the residual R) in a ring of shared-memory stages;
+//                           ragged M / K / N edges are zero-filled by the TMA unit.
+//   warps 2-5 fix-up      : on-chip pass over a landed tile: (BatchNorm affine + activation + SE gate of the producing
+//                           layer for training-mode operands), then the fp32 value v is split in place into
+//                           hi = v with the low 13 mantissa bits cleared (exactly a TF32 number) and lo = v - hi
+//                           (exact in fp32).  hi/lo tiles keep the TMA's swizzled layout, so UMMA reads them as is.
+//   warp 1   MMA issuer   : one thread, tcgen05.mma.cta_group::1.kind::tf32 (M=128, N<=128, K=8):
+//                           hi*hi + lo*hi + hi*lo  -> fp32-grade products (~2^-19, tighter than the bf16x3 kernel),
+//                           accumulators double-buffered in TMEM.  The residual is added BY THE TENSOR CORE:
+//                           R tiles ride the same pipeline as extra k-blocks against a 32x32 identity operand
+//                           (R_hi*I + R_lo*I is exact), so the epilogue never reads global memory.
+//   warps 6-9 epilogue    : tcgen05.ld (32 lanes x 32 columns) -> shift + activation in registers -> 128B-swizzled
+//                           staging tile -> cp.async.bulk.tensor store (ragged edges clipped by the TMA unit).
+//                           BatchNorm batch statistics: each lane sums one column of the staged 32x32 tile and keeps
+//                           its partial sums in registers across all tiles of the CTA.
+// The folded-BatchNorm scale of the epilogue is applied to the WEIGHT rows during their fix-up (W is tiny), which is
+// what lets the residual go through the accumulator unscaled.  Weights whose hi/lo tiles fit stay resident in shared
+// memory for the whole N tile (all layers of mn10 with M >= 512 000 rows); larger K streams W k-blocks with A.
+// HBM-bound at mn10 widths: algorithmic bytes per launch = 4*(M*K + M*N (+ M*N residual) + N*K).
+#include <cuda.h>
+#include <cstdlib>
+
+#include "tc_common.cuh"
+
+// Optional per-role cycle accounting (scripts/timing/: built with -DEAT_TMA_TIMING into a separate library, never part of
+// libeat_b200.so): each role accumulates clock64() deltas between marks; one thread per role and CTA dumps
+// {4 accumulators, count} to the buffer registered with eat_debug_tma_timing().
+#ifdef EAT_TMA_TIMING
+__device__ long long* g_tma_timing = nullptr;
+extern "C" int eat_debug_tma_timing(long long* buf) {
+  return cudaMemcpyToSymbol(g_tma_timing, &buf, sizeof(buf)) == cudaSuccess ? 0 : 2;
+}
+#define TT_DECL long long t_acc[4] = {0, 0, 0, 0}; long long t_prev = clock64(); int t_cnt = 0;
+#define TT_MARK(i) { const long long t_now = clock64(); t_acc[i] += t_now - t_prev; t_prev = t_now; }
+#define TT_COUNT ++t_cnt;
+#define TT_DUMP(role, cond)                                                            \
+  if ((cond) && g_tma_timing != nullptr) {                                             \
+    long long* d__ = g_tma_timing + ((size_t)blockIdx.x * 4 + (role)) * 8;             \
+    for (int i__ = 0; i__ < 4; ++i__) d__[i__] = t_acc[i__];                           \
+    d__[4] = t_cnt;                                                                    \
+  }
+#else
+#define TT_DECL
+#define TT_MARK(i)
+#define TT_COUNT
+#define TT_DUMP(role, cond)
+#endif
+
+namespace {
+using namespace tc;
+
+constexpr int BM = 128;
+constexpr int KB = 32;                  // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int BN_MAX = 128;
+constexpr int A_TILE = BM * 128;        // 16 KB
+constexpr int kThreads = 320;           // TMA warp, MMA warp, 4 fix-up warps, 4 epilogue warps
+constexpr int kMmaWarp = 1, kFirstFix = 2, kFirstEpi = 6;
+constexpr int STG_BYTES = 32 * 128;     // one staged 32 x 32 fp32 sub-tile
+
+struct TmaParams {
+  int M, N, K;
+  int BN, n_tiles, m_tiles, k_blocks, r_blocks;   // r_blocks: residual k-blocks per tile (0: no residual)
+  int stages, wres;                               // wres != 0: weight hi/lo tiles resident per N tile
+  int n_acc, acc_cols, tmem_cols;                 // TMEM accumulators in flight (n_acc * acc_cols <= tmem_cols columns)
+  int stg_bufs;                                   // staging buffers per epilogue warp (1 or 2)
+  uint32_t stage_bytes, off_w, off_ident, off_stg, off_f, off_bar;   // shared-memory carve-up (bytes)
+  int kpad;                                       // floats reserved for each of the in-transform vectors (0: none)
+  const float* in_scale; const float* in_shift; const float* gate; int in_act; int rps;
+  const float* scale; const float* shift;        // epilogue affine (scale is folded into W)
+  double* stat_sum; double* stat_sq;
+};
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B, 8-row groups 1024 B apart (same as pw_tcgen05.cu)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor: D fp32, A/B TF32 (format 2), both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+template <int XACT> __device__ __forceinline__ float act_in(float v) {
+  if (XACT == 1) return fmaxf(v, 0.f);
+  if (XACT == 2) return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+  return v;
+}
+template <int EPI> __device__ __forceinline__ float act_out(float v) {
+  if (EPI == 2) return fmaxf(v, 0.f);
+  if (EPI == 3) return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+  return v;
+}
+// v -> (hi, lo): hi keeps the 10 explicit mantissa bits a TF32 operand has, lo = v - hi is exact in fp32
+__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
+  hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo.x = v.x - hi.x;
+  hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); lo.y = v.y - hi.y;
+  hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo.z = v.z - hi.z;
+  hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = v.w - hi.w;
+}
+
+// ---- fix-up passes over a landed 128-byte-swizzled tile.  128 fix-up threads; a thread owns one 16-byte chunk column c
+// and 2^LG rows (r0 + i * (128 >> LG)); all its loads are issued before the first store (the in-place stores would
+// otherwise serialise the loop: the compiler cannot prove they do not alias the next row's load).
+template <int LG>
+struct FixMap {
+  static constexpr int ROWS = 1 << LG;            // rows per thread
+  static constexpr int RSTEP = 128 >> LG;         // a multiple of 8, so (row & 7) is the same for all rows of a thread
+  static constexpr int STRIDE = RSTEP * 128;      // bytes between a thread's rows
+};
+
+// A-operand tile: optional BatchNorm affine + activation (XACT >= 0) and SE gate, rows >= rows_valid forced to zero
+template <int LG, int XACT>
+__device__ __forceinline__ void fix_a(unsigned char* hi, unsigned char* lo, int ft, int rows_valid, const float* s_isc,
+                                      const float* s_ish, int k, const float* gate, int off0, int b0, int rps, int K) {
+  using M = FixMap<LG>;
+  const int c = ft & ((1 << LG) - 1), r0 = ft >> LG;
+  const uint32_t off = swz(r0, c);
+  float4 v[M::ROWS];
+#pragma unroll
+  for (int i = 0; i < M::ROWS; ++i) v[i] = *reinterpret_cast<const float4*>(hi + off + i * M::STRIDE);
+  if (XACT >= 0) {
+    const float4 isc = *reinterpret_cast<const float4*>(s_isc + k), ish = *reinterpret_cast<const float4*>(s_ish + k);
+#pragma unroll
+    for (int i = 0; i < M::ROWS; ++i) {
+      v[i].x = act_in<XACT>(fmaf(v[i].x, isc.x, ish.x)); v[i].y = act_in<XACT>(fmaf(v[i].y, isc.y, ish.y));
+      v[i].z = act_in<XACT>(fmaf(v[i].z, isc.z, ish.z)); v[i].w = act_in<XACT>(fmaf(v[i].w, isc.w, ish.w));
+      if (r0 + i * M::RSTEP >= rows_valid) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // rows past M stay zero (statistics)
+    }
+  }
+  if (gate != nullptr && k < K) {
+    if (rps >= BM) {
+      // a 128-row tile touches at most two samples: both gate vectors are requested up front (L1/L2 hits) instead of
+      // one dependent load per row
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + (size_t)b0 * K + k));
+      const bool two = off0 + rows_valid > rps;
+      const float4 g1 = two ? __ldg(reinterpret_cast<const float4*>(gate + (size_t)(b0 + 1) * K + k)) : g0;
+#pragma unroll
+      for (int i = 0; i < M::ROWS; ++i) {
+        const float4 g = (off0 + r0 + i * M::RSTEP >= rps) ? g1 : g0;
+        v[i].x *= g.x; v[i].y *= g.y; v[i].z *= g.z; v[i].w *= g.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < M::ROWS; ++i) {
+        const int r = r0 + i * M::RSTEP;
+        if (r < rows_valid) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(gate + (size_t)((off0 + r) / rps + b0) * K + k));
+          v[i].x *= g.x; v[i].y *= g.y; v[i].z *= g.z; v[i].w *= g.w;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < M::ROWS; ++i) {
+    float4 h, l;
+    split4(v[i], h, l);
+    *reinterpret_cast<float4*>(hi + off + i * M::STRIDE) = h;
+    *reinterpret_cast<float4*>(lo + off + i * M::STRIDE) = l;
+  }
+}
+
+// weight tile [rows < BN]: row n scaled by the folded-BatchNorm scale of the epilogue (FOLD), split hi/lo
+template <int LG, bool FOLD>
+__device__ __forceinline__ void fix_w(unsigned char* hi, unsigned char* lo, int ft, int BN, const float* scale, int n0, int N) {
+  using M = FixMap<LG>;
+  const int c = ft & ((1 << LG) - 1), r0 = ft >> LG;
+  const uint32_t off = swz(r0, c);
+  float4 v[M::ROWS];
+  float sc[M::ROWS];
+#pragma unroll
+  for (int i = 0; i < M::ROWS; ++i) {
+    const int r = r0 + i * M::RSTEP;
+    v[i] = r < BN ? *reinterpret_cast<const float4*>(hi + off + i * M::STRIDE) : make_float4(0.f, 0.f, 0.f, 0.f);
+    sc[i] = (FOLD && r < BN && n0 + r < N) ? __ldg(scale + n0 + r) : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < M::ROWS; ++i) {
+    const int r = r0 + i * M::RSTEP;
+    if (r < BN) {
+      if (FOLD) { v[i].x *= sc[i]; v[i].y *= sc[i]; v[i].z *= sc[i]; v[i].w *= sc[i]; }
+      float4 h, l;
+      split4(v[i], h, l);
+      *reinterpret_cast<float4*>(hi + off + i * M::STRIDE) = h;
+      *reinterpret_cast<float4*>(lo + off + i * M::STRIDE) = l;
+    }
+  }
+}
+
+__device__ __forceinline__ int chunk_lg(int krem) {          // log2 of the 16-byte chunks (rounded up to 2 / 4 / 8) of a k-block
+  const int nch = krem >= KB ? 8 : (krem + 3) >> 2;
+  return nch <= 2 ? 1 : (nch <= 4 ? 2 : 3);
+}
+
+// EPI : 0 raw output (+ statistics), 1 + shift, 2 + shift + ReLU, 3 + shift + Hardswish   (scale lives in W)
+// XACT: -1 raw operand (gate still possible), 0 affine, 1 affine + ReLU, 2 affine + Hardswish on load
+template <int EPI, int XACT>
+__global__ void __launch_bounds__(kThreads, 2)
+pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
+              const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapR, const TmaParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* s_w = smem + p.off_w;                   // resident weights: [k_blocks][hi | lo][BN rows x 128 B]
+  unsigned char* s_ident = smem + p.off_ident;           // 32 x 32 identity, K-major, swizzled (4 KB; residual launches)
+  unsigned char* s_stg = smem + p.off_stg;               // [4 epilogue warps][stg_bufs][4 KB]
+  float* s_isc = reinterpret_cast<float*>(smem + p.off_f);             // [kpad] in-transform scale (0 beyond K)
+  float* s_ish = s_isc + p.kpad;                                       // [kpad]
+  float* s_shift = s_ish + p.kpad;                                     // [BN_MAX] epilogue shift of the current N tile
+  float* s_stat = s_shift + BN_MAX;                                    // [4][2][BN_MAX]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  const int S = p.stages;
+  const uint32_t bar_full = smem_u32(bars), bar_ready = bar_full + 8 * S, bar_empty = bar_ready + 8 * S;
+  const uint32_t bar_tfull = bar_empty + 8 * S, bar_tempty = bar_tfull + 64, bar_wfull = bar_tempty + 64;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 3 * S + 17);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_ready + 8 * s, 4); mbar_init(bar_empty + 8 * s, 1); }
+    for (int a = 0; a < 8; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+    mbar_init(bar_wfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapW)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapC)) : "memory");
+  }
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  // one-time tables: identity operand for the residual MMAs, in-transform vectors (zero beyond K: act(0) = 0)
+  if (p.r_blocks > 0) {
+    for (int i = threadIdx.x; i < 32 * 8; i += kThreads) {             // 32 rows x 8 chunks
+      const int r = i >> 3, c = i & 7;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((r >> 2) == c) { if ((r & 3) == 0) v.x = 1.f; else if ((r & 3) == 1) v.y = 1.f; else if ((r & 3) == 2) v.z = 1.f; else v.w = 1.f; }
+      *reinterpret_cast<float4*>(s_ident + swz(r, c)) = v;
+    }
+  }
+  if (XACT >= 0) {
+    for (int i = threadIdx.x; i < p.kpad; i += kThreads) {
+      s_isc[i] = i < p.K ? p.in_scale[i] : 0.f;
+      s_ish[i] = i < p.K ? p.in_shift[i] : 0.f;
+    }
+  }
+  for (int i = threadIdx.x; i < 8 * BN_MAX; i += kThreads) s_stat[i] = 0.f;
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int BN = p.BN;
+  const int kb_total = p.k_blocks + p.r_blocks;          // pipeline slots per tile
+  const uint32_t w_tile = (uint32_t)BN * 128u;           // bytes of one [BN x 32] weight tile
+  const uint32_t stage_base = smem_u32(smem);
+  // tile walk without divisions (m fastest: a CTA stays on one N tile while it can)
+  int nt = blockIdx.x / p.m_tiles, mt = blockIdx.x - nt * p.m_tiles;
+  auto next_tile = [&]() { mt += gridDim.x; while (mt >= p.m_tiles) { mt -= p.m_tiles; ++nt; } };
+
+  if (warp == 0) {
+    // ================================================================= TMA producer (one thread)
+    if (lane == 0) {
+      int s = 0, s_prev = 0, cur_nt = -1;
+      uint32_t ph = 0, ph_prev = 0;
+      bool first = true;
+      TT_DECL
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int m0 = mt * BM, n0 = nt * BN;
+        if (p.wres && nt != cur_nt) {
+          // every MMA that reads the old weights has retired once the most recently filled stage was released
+          if (!first) mbar_wait(bar_empty + 8 * s_prev, ph_prev);
+          mbar_expect_tx(bar_wfull, (uint32_t)p.k_blocks * w_tile);
+          for (int kb = 0; kb < p.k_blocks; ++kb)
+            tma_load_2d(&mapW, bar_wfull, smem_u32(s_w) + (uint32_t)kb * 2u * w_tile, kb * KB, n0);
+          cur_nt = nt;
+        }
+        next_tile();
+        for (int kb = 0; kb < kb_total; ++kb) {
+          TT_MARK(0)
+          mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+          TT_MARK(1)
+          const uint32_t dst = stage_base + (uint32_t)s * p.stage_bytes;
+          if (kb < p.k_blocks) {
+            mbar_expect_tx(bar_full + 8 * s, A_TILE + (p.wres ? 0u : w_tile));
+            tma_load_2d(&mapA, bar_full + 8 * s, dst, kb * KB, m0);
+            if (!p.wres) tma_load_2d(&mapW, bar_full + 8 * s, dst + 2 * A_TILE, kb * KB, n0);
+          } else {
+            mbar_expect_tx(bar_full + 8 * s, A_TILE);
+            tma_load_2d(&mapR, bar_full + 8 * s, dst, n0 + (kb - p.k_blocks) * KB, m0);
+          }
+          TT_MARK(2)
+          s_prev = s; ph_prev = ph; first = false;
+          if (++s == S) { s = 0; ph ^= 1u; }
+        }
+        TT_COUNT
+      }
+      TT_DUMP(0, true)
+    }
+    __syncwarp();
+  } else if (warp == kMmaWarp) {
+    // ================================================================= MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(BN), idesc_id = idesc_tf32(32);
+      const uint64_t desc0 = umma_desc(0);                   // descriptor of address 0: add (address >> 4)
+      const uint64_t ident = desc0 + (smem_u32(s_ident) >> 4);
+      const uint64_t wres0 = desc0 + (smem_u32(s_w) >> 4);
+      const uint32_t w_tile16 = w_tile >> 4;
+      int s = 0, acc = 0;
+      uint32_t ph = 0, acc_phase = 0;
+      TT_DECL
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        TT_MARK(0)
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);
+        TT_MARK(1)
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.acc_cols);
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(bar_ready + 8 * s, ph);
+          TT_MARK(2)
+          tc_fence_after();
+          const uint32_t sa = stage_base + (uint32_t)s * p.stage_bytes;
+          const uint64_t a_hi = desc0 + (sa >> 4), a_lo = a_hi + (A_TILE >> 4);
+          if (kb < p.k_blocks) {
+            const uint64_t w_hi = p.wres ? wres0 + (uint32_t)kb * 2u * w_tile16 : a_hi + (2 * A_TILE >> 4);
+            const uint64_t w_lo = w_hi + w_tile16;
+            const int krem = p.K - kb * KB;
+            const int nk8 = krem >= KB ? KB / 8 : (krem + 7) >> 3;
+#pragma unroll
+            for (int k8 = 0; k8 < 4; ++k8) {
+              if (k8 < nk8) {
+                const uint64_t ko = (uint64_t)(k8 * 2);             // 8 tf32 = 32 bytes along K, in 16-byte units
+                mma_tf32(tmem_d, a_hi + ko, w_hi + ko, idesc, (kb | k8) ? 1u : 0u);
+                mma_tf32(tmem_d, a_lo + ko, w_hi + ko, idesc, 1u);
+                mma_tf32(tmem_d, a_hi + ko, w_lo + ko, idesc, 1u);
+              }
+            }
+          } else {                 // residual block j: D[:, 32j .. 32j+31] += R_hi . I + R_lo . I
+            const uint32_t tmem_r = tmem_d + (uint32_t)(kb - p.k_blocks) * 32u;
+#pragma unroll
+            for (int k8 = 0; k8 < 4; ++k8) {
+              const uint64_t ko = (uint64_t)(k8 * 2);
+              mma_tf32(tmem_r, a_hi + ko, ident + ko, idesc_id, 1u);
+              mma_tf32(tmem_r, a_lo + ko, ident + ko, idesc_id, 1u);
+            }
+          }
+          tc_commit(bar_empty + 8 * s);
+          if (++s == S) { s = 0; ph ^= 1u; }
+        }
+        tc_commit(bar_tfull + 8 * acc);
+        TT_MARK(3)
+        TT_COUNT
+        if (++acc == p.n_acc) { acc = 0; acc_phase ^= 1u; }
+      }
+      TT_DUMP(1, true)
+    }
+    __syncwarp();
+  } else if (warp < kFirstEpi) {
+    // ================================================================= fix-up warps (128 threads)
+    const int ft = threadIdx.x - kFirstFix * 32;
+    int s = 0, cur_nt = -1;
+    uint32_t ph = 0, wphase = 0;
+    const bool fold = EPI != 0 && p.scale != nullptr;
+    auto do_fix_w = [&](unsigned char* w_hi, int kb, int n0) {
+      const int lg = chunk_lg(p.K - kb * KB);
+      unsigned char* w_lo = w_hi + w_tile;
+      if (fold) {
+        if (lg == 3) fix_w<3, true>(w_hi, w_lo, ft, BN, p.scale, n0, p.N);
+        else if (lg == 2) fix_w<2, true>(w_hi, w_lo, ft, BN, p.scale, n0, p.N);
+        else fix_w<1, true>(w_hi, w_lo, ft, BN, p.scale, n0, p.N);
+      } else {
+        if (lg == 3) fix_w<3, false>(w_hi, w_lo, ft, BN, nullptr, n0, p.N);
+        else if (lg == 2) fix_w<2, false>(w_hi, w_lo, ft, BN, nullptr, n0, p.N);
+        else fix_w<1, false>(w_hi, w_lo, ft, BN, nullptr, n0, p.N);
+      }
+    };
+    TT_DECL
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int m0 = mt * BM, n0 = nt * BN;
+      const int rows_valid = min(BM, p.M - m0);
+      if (p.wres && nt != cur_nt) {
+        mbar_wait(bar_wfull, wphase);
+        wphase ^= 1u;
+        for (int kb = 0; kb < p.k_blocks; ++kb) do_fix_w(s_w + (size_t)kb * 2 * w_tile, kb, n0);
+        cur_nt = nt;
+      }
+      next_tile();
+      int b0 = 0, off0 = 0;
+      if (p.gate != nullptr) { b0 = m0 / p.rps; off0 = m0 - b0 * p.rps; }
+      for (int kb = 0; kb < kb_total; ++kb) {
+        TT_MARK(0)
+        mbar_wait(bar_full + 8 * s, ph);
+        TT_MARK(1)
+        unsigned char* a_hi = smem + (size_t)s * p.stage_bytes;
+        unsigned char* a_lo = a_hi + A_TILE;
+        if (kb >= p.k_blocks) {
+          fix_a<3, -1>(a_hi, a_lo, ft, BM, nullptr, nullptr, 0, nullptr, 0, 0, 1, 0);            // residual tile: plain split
+        } else {
+          const int lg = chunk_lg(p.K - kb * KB);
+          const int k = kb * KB + (ft & ((1 << lg) - 1)) * 4;
+          if (lg == 3) fix_a<3, XACT>(a_hi, a_lo, ft, rows_valid, s_isc, s_ish, k, p.gate, off0, b0, p.rps, p.K);
+          else if (lg == 2) fix_a<2, XACT>(a_hi, a_lo, ft, rows_valid, s_isc, s_ish, k, p.gate, off0, b0, p.rps, p.K);
+          else fix_a<1, XACT>(a_hi, a_lo, ft, rows_valid, s_isc, s_ish, k, p.gate, off0, b0, p.rps, p.K);
+          if (!p.wres) do_fix_w(a_hi + 2 * A_TILE, kb, n0);
+        }
+        TT_MARK(2)
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_ready + 8 * s);
+        TT_MARK(3)
+        if (++s == S) { s = 0; ph ^= 1u; }
+      }
+      TT_COUNT
+    }
+    TT_DUMP(2, ft == 0)
+  } else {
+    // ================================================================= epilogue (one warp per TMEM lane quadrant)
+    const int q = warp & 3;                                   // TMEM lane quadrant this warp may access
+    const int ew = warp - kFirstEpi;
+    const int etid = threadIdx.x - kFirstEpi * 32;            // 0..127
+    unsigned char* stg = s_stg + (size_t)ew * p.stg_bufs * STG_BYTES;
+    float* my_stat = s_stat + ew * 2 * BN_MAX;
+    const bool do_stats = EPI == 0 && p.stat_sum != nullptr;
+    float csum[4] = {0.f, 0.f, 0.f, 0.f}, csq[4] = {0.f, 0.f, 0.f, 0.f};
+    int cur_nt = -1, acc = 0, cb = 0;
+    uint32_t acc_phase = 0;
+    TT_DECL
+    auto flush_stats = [&](int nt_old) {
+      // lane partials -> shared, combine the four warps, one fp64 atomic per channel
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { my_stat[c * 32 + lane] = csum[c]; my_stat[BN_MAX + c * 32 + lane] = csq[c]; csum[c] = 0.f; csq[c] = 0.f; }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (etid < BN) {
+        const int n = nt_old * BN + etid;
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { a += s_stat[w * 2 * BN_MAX + etid]; b += s_stat[w * 2 * BN_MAX + BN_MAX + etid]; }
+        if (n < p.N) { atomicAdd(p.stat_sum + n, (double)a); atomicAdd(p.stat_sq + n, (double)b); }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int m0 = mt * BM, n0 = nt * BN;
+      if (nt != cur_nt) {
+        if (do_stats && cur_nt >= 0) flush_stats(cur_nt);
+        if (EPI != 0) {
+          asm volatile("bar.sync 2, 128;" ::: "memory");       // everyone is done with the previous tile's shifts
+          if (etid < BN) s_shift[etid] = (p.shift != nullptr && n0 + etid < p.N) ? p.shift[n0 + etid] : 0.f;
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+        }
+        cur_nt = nt;
+      }
+      next_tile();
+      TT_MARK(0)
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      TT_MARK(1)
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_cols);
+      const int row0 = m0 + q * 32;
+      const int rows_left = min(32, p.M - row0);              // <= 0: nothing of this warp's slab is inside M
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c * 32 < BN && n0 + c * 32 < p.N) {
+          unsigned char* buf = stg + (size_t)cb * STG_BYTES;
+          // the store issued from this buffer (two chunks ago, or the previous one with a single buffer) has drained
+          if (p.stg_bufs == 2) { cb ^= 1; if (lane == 0) tma_wait_read<1>(); }
+          else if (lane == 0) tma_wait_read<0>();
+          __syncwarp();
+          uint32_t raw[32];
+          tc_ld32(trow + c * 32, raw);
+          TT_MARK(2)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 v = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                                   __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
+            if (EPI != 0) {
+              const float4 sh = *reinterpret_cast<const float4*>(s_shift + c * 32 + 4 * j);
+              v.x = act_out<EPI>(v.x + sh.x); v.y = act_out<EPI>(v.y + sh.y);
+              v.z = act_out<EPI>(v.z + sh.z); v.w = act_out<EPI>(v.w + sh.w);
+            }
+            *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = v;     // row = lane, chunk j, swizzled
+          }
+          if (do_stats) {
+            __syncwarp();
+            // lane = column: sum the staged column over the rows of this slab that lie inside M (conflict-free:
+            // the 32 lanes of a row read 32 different banks)
+            float s1 = 0.f, s2 = 0.f;
+            const int cj = lane >> 2, ci = lane & 3;
+            if (rows_left >= 32) {
+#pragma unroll
+              for (int r = 0; r < 32; ++r) {
+                const float x = *reinterpret_cast<const float*>(buf + r * 128 + ((cj ^ (r & 7)) << 4) + ci * 4);
+                s1 += x; s2 = fmaf(x, x, s2);
+              }
+            } else {
+              for (int r = 0; r < rows_left; ++r) {
+                const float x = *reinterpret_cast<const float*>(buf + r * 128 + ((cj ^ (r & 7)) << 4) + ci * 4);
+                s1 += x; s2 = fmaf(x, x, s2);
+              }
+            }
+            csum[c] += s1; csq[c] += s2;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && rows_left > 0) { tma_store_2d(&mapC, smem_u32(buf), n0 + c * 32, row0); tma_commit(); }
+          TT_MARK(3)
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      TT_COUNT
+      if (++acc == p.n_acc) { acc = 0; acc_phase ^= 1u; }
+    }
+    TT_DUMP(3, ew == 0 && lane == 0)
+    if (do_stats && cur_nt >= 0) flush_stats(cur_nt);
+    if (lane == 0) tma_wait_read<0>();                        // staging buffers must outlive their stores
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// [rows, cols] fp32 row-major tensor, box = box_rows x 32 columns (128 bytes), SWIZZLE_128B, zero fill outside
+int make_map(CUtensorMap* map, const void* ptr, long long rows, int cols, int box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  if (enc == nullptr) { eat_set_error("pw_tma: cuTensorMapEncodeTiled is not available from this driver"); return EAT_ERR_CUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)cols * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { eat_set_error("pw_tma: cuTensorMapEncodeTiled failed (pointer / stride alignment?)"); return EAT_ERR_CUDA; }
+  return EAT_OK;
+}
+
+constexpr size_t kSmemLimit = 227 * 1024;
+
+template <int EPI, int XACT>
+int launch_tma(const void* A, const float* W, void* C, const void* R, TmaParams p, cudaStream_t st) {
+  // ---- tiling
+  if (p.N <= BN_MAX) { p.BN = ceil_div(p.N, 16) * 16; p.n_tiles = 1; }
+  else {                                   // several N tiles: multiples of 32 so that no store chunk straddles two tiles
+    int best = 128, best_pad = ceil_div(p.N, 128) * 128;
+    for (int bn : {96, 64}) { const int pad = ceil_div(p.N, bn) * bn; if (pad < best_pad) { best = bn; best_pad = pad; } }
+    p.BN = best; p.n_tiles = ceil_div(p.N, best);
+  }
+  p.m_tiles = ceil_div(p.M, BM);
+  p.k_blocks = ceil_div(p.K, KB);
+  p.r_blocks = R != nullptr ? ceil_div(min(p.BN, p.N), 32) : 0;
+  p.kpad = XACT >= 0 ? p.k_blocks * KB : 0;
+  // ---- shared-memory carve-up: [stages][resident W][identity][staging][floats][barriers].
+  // Preferred: TWO co-resident CTAs per SM (<= 113 KB each, 256 TMEM columns each): every per-tile latency chain
+  // (single-thread TMA / MMA issue, fix-up, TMEM read-out) is then overlapped by a second, independent tile stream.
+  // Needs resident weights and >= 2 stages; otherwise one CTA takes the whole SM.
+  const size_t w_tile = (size_t)p.BN * 128;
+  const size_t w_res = (size_t)p.k_blocks * 2 * w_tile;
+  const size_t ident = p.r_blocks > 0 ? 4096 : 0;
+  const size_t floats = (2 * (size_t)p.kpad + BN_MAX + 8 * BN_MAX) * 4;
+  const size_t barsz = (3 * 8 + 17) * 8 + 16;
+  auto fixed = [&](int bufs) { return ident + (size_t)bufs * 4 * STG_BYTES + floats + barsz + 1024 /*alignment slack*/; };
+  int ctas = 1;
+  p.stg_bufs = 2;
+  const char* force = getenv("EAT_TMA_CTAS");
+  const size_t half = (kSmemLimit - 2048) / 2;
+  if (!(force && atoi(force) == 1)) {
+    for (int bufs = 2; bufs >= 1 && ctas == 1; --bufs)
+      if (fixed(bufs) + w_res + 2 * (size_t)(2 * A_TILE) <= half) { ctas = 2; p.stg_bufs = bufs; }
+  }
+  const size_t limit = ctas == 2 ? half : kSmemLimit;
+  p.wres = ctas == 2 ? 1 : ((fixed(2) + w_res + 3 * (size_t)(2 * A_TILE) <= kSmemLimit) ? 1 : 0);
+  p.stage_bytes = (uint32_t)(2 * A_TILE + (p.wres ? 0 : 2 * w_tile));
+  const size_t avail = limit - fixed(p.stg_bufs) - (p.wres ? w_res : 0);
+  p.stages = (int)(avail / p.stage_bytes);
+  if (p.stages > 8) p.stages = 8;
+  if (p.stages < 2) { eat_set_error("pw_tma: shared-memory budget exceeded (K too large for the in-transform tables)"); return EAT_ERR_UNSUPPORTED; }
+  // TMEM: n_acc accumulators of acc_cols (>= BN) columns; 256 columns per CTA when two CTAs share the SM
+  p.tmem_cols = ctas == 2 ? 256 : 512;
+  p.acc_cols = p.BN <= 32 ? 32 : (p.BN <= 64 ? 64 : 128);
+  p.n_acc = p.tmem_cols / p.acc_cols;
+  if (p.n_acc > 8) p.n_acc = 8;
+  if (const char* e = getenv("EAT_TMA_NACC")) { const int v = atoi(e); if (v >= 1 && v <= p.n_acc) p.n_acc = v; }
+  size_t off = (size_t)p.stages * p.stage_bytes;
+  p.off_w = (uint32_t)off; off += p.wres ? w_res : 0;
+  p.off_ident = (uint32_t)off; off += ident;
+  p.off_stg = (uint32_t)off; off += (size_t)p.stg_bufs * 4 * STG_BYTES;
+  p.off_f = (uint32_t)off; off += floats;
+  off = (off + 7) & ~(size_t)7;
+  p.off_bar = (uint32_t)off; off += (3 * (size_t)p.stages + 17) * 8 + 16;
+  const size_t smem = off;
+  if (smem > limit) { eat_set_error("pw_tma: shared-memory carve-up exceeds its budget"); return EAT_ERR_UNSUPPORTED; }
+  // ---- tensor maps
+  CUtensorMap mA, mW, mC, mR;
+  if (int rc = make_map(&mA, A, p.M, p.K, BM)) return rc;
+  if (int rc = make_map(&mW, W, p.N, p.K, p.BN)) return rc;
+  if (int rc = make_map(&mC, C, p.M, p.N, 32)) return rc;
+  if (int rc = make_map(&mR, R != nullptr ? R : C, p.M, p.N, BM)) return rc;
+  static unsigned long long attr_mask = 0;
+  if (int rc = eat_opt_in_smem(pw_tma_kernel<EPI, XACT>, kSmemLimit, attr_mask)) return rc;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int slots = sms * ctas;
+  pw_tma_kernel<EPI, XACT><<<tiles < slots ? tiles : slots, kThreads, smem, st>>>(mA, mW, mC, mR, p);
+  EAT_CHECK_LAUNCH();
+  return EAT_OK;
+}
+
+template <int EPI>
+int launch_tma_x(const void* A, const float* W, void* C, const void* R, const TmaParams& p, cudaStream_t st) {
+  if (p.in_scale == nullptr) return launch_tma<EPI, -1>(A, W, C, R, p, st);
+  if (p.in_act == EAT_ACT_RELU) return launch_tma<EPI, 1>(A, W, C, R, p, st);
+  if (p.in_act == EAT_ACT_HSWISH) return launch_tma<EPI, 2>(A, W, C, R, p, st);
+  return launch_tma<EPI, 0>(A, W, C, R, p, st);
+}
+
+}  // namespace
+
+extern "C" int eat_pw_tma_fwd(const float* A, const float* W, float* C, long long M, int N, int K, const float* in_scale,
+                              const float* in_shift, int in_act, const float* gate, int rows_per_sample,
+                              const float* scale, const float* shift, int act, const float* residual, double* stat_sum,
+                              double* stat_sq, cudaStream_t st) {
+  if (M == 0) return EAT_OK;
+  if (act == EAT_ACT_SIGMOID || in_act == EAT_ACT_SIGMOID) { eat_set_error("pw_tma: sigmoid epilogues run on the CUDA-core GEMM (eat_gemm_simt_fwd)"); return EAT_ERR_UNSUPPORTED; }
+  const bool aff = scale != nullptr || shift != nullptr || act != 0;
+  if (residual != nullptr && act != EAT_ACT_NONE) { eat_set_error("pw_tma: the residual is accumulated before the activation; residual + activation is not offered"); return EAT_ERR_UNSUPPORTED; }
+  if (stat_sum != nullptr && (aff || residual != nullptr)) {
+    eat_set_error("pw_tma: batch statistics are produced by the raw-output variant only (no affine/activation/residual)");
+    return EAT_ERR_UNSUPPORTED;
+  }
+  if ((in_scale == nullptr) != (in_shift == nullptr)) { eat_set_error("pw_tma: in_scale and in_shift come together"); return EAT_ERR_ARG; }
+  if (K % 4 != 0 || N % 4 != 0) { eat_set_error("pw_tma: K and N must be multiples of 4 (16-byte row pitch for TMA)"); return EAT_ERR_ARG; }
+  if (M >= (1ll << 31) - BM) { eat_set_error("pw_tma: M too large"); return EAT_ERR_ARG; }
+  if ((((uintptr_t)A) | ((uintptr_t)W) | ((uintptr_t)C) | ((uintptr_t)residual) | ((uintptr_t)gate)) & 15) { eat_set_error("pw_tma: operands must be 16-byte aligned"); return EAT_ERR_ARG; }
+  TmaParams p{};
+  p.M = (int)M; p.N = N; p.K = K;
+  p.in_scale = in_scale; p.in_shift = in_shift; p.gate = gate; p.in_act = in_act; p.rps = rows_per_sample > 0 ? rows_per_sample : 1;
+  p.scale = scale; p.shift = shift; p.stat_sum = stat_sum; p.stat_sq = stat_sq;
+  if (!aff) return launch_tma_x<0>(A, W, C, residual, p, st);
+  if (act == EAT_ACT_RELU) return launch_tma_x<2>(A, W, C, residual, p, st);
+  if (act == EAT_ACT_HSWISH) return launch_tma_x<3>(A, W, C, residual, p, st);
+  return launch_tma_x<1>(A, W, C, residual, p, st);
+}

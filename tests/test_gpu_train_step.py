@@ -133,7 +133,7 @@ def test_trainer_step_matches_reference_loop_with_autograd(graph):
     test_trainer_cuda_graph_matches_eager_steps) flip -- a wrong schedule factor, bias correction or 1/world would be
     a 10-100 % error; the Adam arithmetic itself is pinned to 2e-6 in test_adam_kernel_matches_torch_optim.  A tensor
     whose true gradient is 0 (a BatchNorm bias feeding a 1x1 conv + training-mode BatchNorm) random-walks on fp32
-    summation noise in both implementations; those are skipped by their gradient norm, < 1e-6 of the largest."""
+    summation noise in both implementations; those are skipped by their gradient norm, < 1e-5 of the largest."""
     from efficientat_b200.synth import synth_labels, synth_waveform
     B = 4
     sched = exp_warmup_linear_down(2, 4, 1, 0.1)
@@ -180,7 +180,7 @@ def test_trainer_step_matches_reference_loop_with_autograd(graph):
     gmax = max(gnorm.values())
     worst, skipped = 0.0, 0
     for n, p in model2.named_parameters():
-        if gnorm[n] < 1e-6 * gmax:
+        if gnorm[n] < 1e-5 * gmax:
             skipped += 1
             continue
         d = p.detach() - p_before[n]
