@@ -1,4 +1,4 @@
-// Pointwise (1x1) convolution / Linear for fp32 activations as a TMA-fed tcgen05 GEMM (sm_100a):
+// Pointwise (1x1) convolution / Linear for fp32 activations as a TMA-fed tcgen05 GEMM (sm_100a), bf16x3 products:
 //     C[M,N] = epi( xf(A)[M,K] . W[N,K]^T  (+ R[M,N]) )          A, C, R: NHWC activation rows, fp32; W: fp32
 // Same contract and reference call sites as pw_tcgen05.cu (models/mn/block_types.py:140-147,167-171;
 // models/mn/model.py:160-166; every data-gradient GEMM of loss.backward(), ex_audioset.py:197).
@@ -11,14 +11,16 @@
 //                           [128 rows x 32 k] (and of W, and of the residual R) in a ring of shared-memory stages;
 //                           ragged M / K / N edges are zero-filled by the TMA unit.
 //   warps 2-5 fix-up      : on-chip pass over a landed tile: (BatchNorm affine + activation + SE gate of the producing
-//                           layer for training-mode operands), then the fp32 value v is split in place into
-//                           hi = v with the low 13 mantissa bits cleared (exactly a TF32 number) and lo = v - hi
-//                           (exact in fp32).  hi/lo tiles keep the TMA's swizzled layout, so UMMA reads them as is.
-//   warp 1   MMA issuer   : one thread, tcgen05.mma.cta_group::1.kind::tf32 (M=128, N<=128, K=8):
-//                           hi*hi + lo*hi + hi*lo  -> fp32-grade products (~2^-19, tighter than the bf16x3 kernel),
-//                           accumulators double-buffered in TMEM.  The residual is added BY THE TENSOR CORE:
-//                           R tiles ride the same pipeline as extra k-blocks against a 32x32 identity operand
-//                           (R_hi*I + R_lo*I is exact), so the epilogue never reads global memory.
+//                           layer for training-mode operands), then the 32 fp32 values of a row (128 bytes) are
+//                           replaced IN PLACE by 32 bf16 "hi" values (64 bytes) followed by 32 bf16 "lo" values with
+//                           hi + lo = v to ~2^-17 -- the row is then a 64-element bf16 K-major row of the same
+//                           128-byte-swizzled tile the TMA wrote, which UMMA reads as is.  No second buffer: a
+//                           pipeline stage is 16 KB, which is what lets two CTAs share an SM.
+//   warp 1   MMA issuer   : one thread, tcgen05.mma.cta_group::1.kind::f16 (bf16, M=128, N<=128, K=16).  The three
+//                           products hi*hi + lo*hi + hi*lo (fp32-grade, ~2^-16) are three MMAs whose A / B descriptors
+//                           simply point at the hi or lo half of the row; accumulators live in TMEM, several in
+//                           flight.  The residual is added BY THE TENSOR CORE: R tiles ride the same pipeline as extra
+//                           k-blocks against a 32x32 identity operand, so the epilogue never reads global memory.
 //   warps 6-9 epilogue    : tcgen05.ld (32 lanes x 32 columns) -> shift + activation in registers -> 128B-swizzled
 //                           staging tile -> cp.async.bulk.tensor store (ragged edges clipped by the TMA unit).
 //                           BatchNorm batch statistics: each lane sums one column of the staged 32x32 tile and keeps
@@ -89,16 +91,16 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// instruction descriptor: D fp32, A/B TF32 (format 2), both K-major, M = 128, N = n
-__device__ __forceinline__ uint32_t idesc_tf32(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// instruction descriptor: D fp32, A/B bf16 (format 1), both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -128,105 +130,135 @@ template <int EPI> __device__ __forceinline__ float act_out(float v) {
   if (EPI == 3) return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
   return v;
 }
-// v -> (hi, lo): hi keeps the 10 explicit mantissa bits a TF32 operand has, lo = v - hi is exact in fp32
-__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
-  hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo.x = v.x - hi.x;
-  hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); lo.y = v.y - hi.y;
-  hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo.z = v.z - hi.z;
-  hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = v.w - hi.w;
+// 8 fp32 values -> 8 bf16 hi (one 16-byte chunk) + 8 bf16 lo with hi + lo = v to ~2^-17
+__device__ __forceinline__ void split8(const float4 a, const float4 b, uint4& hi, uint4& lo) {
+  hi.x = pack_bf16(a.x, a.y); hi.y = pack_bf16(a.z, a.w); hi.z = pack_bf16(b.x, b.y); hi.w = pack_bf16(b.z, b.w);
+  // bf16 -> fp32 is a 16-bit shift: element 0 of a pair sits in the low half
+  lo.x = pack_bf16(a.x - __uint_as_float(hi.x << 16), a.y - __uint_as_float(hi.x & 0xFFFF0000u));
+  lo.y = pack_bf16(a.z - __uint_as_float(hi.y << 16), a.w - __uint_as_float(hi.y & 0xFFFF0000u));
+  lo.z = pack_bf16(b.x - __uint_as_float(hi.z << 16), b.y - __uint_as_float(hi.z & 0xFFFF0000u));
+  lo.w = pack_bf16(b.z - __uint_as_float(hi.w << 16), b.w - __uint_as_float(hi.w & 0xFFFF0000u));
 }
 
-// ---- fix-up passes over a landed 128-byte-swizzled tile.  128 fix-up threads; a thread owns one 16-byte chunk column c
-// and 2^LG rows (r0 + i * (128 >> LG)); all its loads are issued before the first store (the in-place stores would
-// otherwise serialise the loop: the compiler cannot prove they do not alias the next row's load).
+// ---- fix-up passes over a landed 128-byte-swizzled fp32 tile [rows][32 k].  128 fix-up threads; a thread owns the chunk
+// PAIR cp (fp32 chunks 2cp, 2cp+1 = 8 consecutive k) of 2^LG rows (r0 + i * (128 >> LG)) and writes, into the SAME row,
+// the bf16 hi chunk at logical position cp and the lo chunk at 4 + cp.  The threads of a row are neighbouring lanes of
+// one warp: all loads are issued first, a __syncwarp separates them from the in-place stores.
 template <int LG>
 struct FixMap {
-  static constexpr int ROWS = 1 << LG;            // rows per thread
+  static constexpr int ROWS = 1 << LG;            // rows per thread (= threads per row: 1, 2 or 4 chunk pairs)
   static constexpr int RSTEP = 128 >> LG;         // a multiple of 8, so (row & 7) is the same for all rows of a thread
   static constexpr int STRIDE = RSTEP * 128;      // bytes between a thread's rows
 };
 
 // A-operand tile: optional BatchNorm affine + activation (XACT >= 0) and SE gate, rows >= rows_valid forced to zero
 template <int LG, int XACT>
-__device__ __forceinline__ void fix_a(unsigned char* hi, unsigned char* lo, int ft, int rows_valid, const float* s_isc,
-                                      const float* s_ish, int k, const float* gate, int off0, int b0, int rps, int K) {
+__device__ __forceinline__ void fix_a(unsigned char* tile, int ft, int rows_valid, const float* s_isc, const float* s_ish,
+                                      int k, const float* gate, int off0, int b0, int rps, int K) {
   using M = FixMap<LG>;
-  const int c = ft & ((1 << LG) - 1), r0 = ft >> LG;
-  const uint32_t off = swz(r0, c);
-  float4 v[M::ROWS];
+  const int cp = ft & ((1 << LG) - 1), r0 = ft >> LG;
+  const uint32_t row_off = (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128);
+  const int x = r0 & 7;
+  const uint32_t in0 = row_off + (((2 * cp) ^ x) << 4), in1 = row_off + (((2 * cp + 1) ^ x) << 4);
+  const uint32_t out_hi = row_off + ((cp ^ x) << 4), out_lo = row_off + (((4 + cp) ^ x) << 4);
+  float4 va[M::ROWS], vb[M::ROWS];
 #pragma unroll
-  for (int i = 0; i < M::ROWS; ++i) v[i] = *reinterpret_cast<const float4*>(hi + off + i * M::STRIDE);
+  for (int i = 0; i < M::ROWS; ++i) {
+    va[i] = *reinterpret_cast<const float4*>(tile + in0 + i * M::STRIDE);
+    vb[i] = *reinterpret_cast<const float4*>(tile + in1 + i * M::STRIDE);
+  }
   if (XACT >= 0) {
-    const float4 isc = *reinterpret_cast<const float4*>(s_isc + k), ish = *reinterpret_cast<const float4*>(s_ish + k);
+    const float4 sa = *reinterpret_cast<const float4*>(s_isc + k), sb = *reinterpret_cast<const float4*>(s_isc + k + 4);
+    const float4 ha = *reinterpret_cast<const float4*>(s_ish + k), hb = *reinterpret_cast<const float4*>(s_ish + k + 4);
 #pragma unroll
     for (int i = 0; i < M::ROWS; ++i) {
-      v[i].x = act_in<XACT>(fmaf(v[i].x, isc.x, ish.x)); v[i].y = act_in<XACT>(fmaf(v[i].y, isc.y, ish.y));
-      v[i].z = act_in<XACT>(fmaf(v[i].z, isc.z, ish.z)); v[i].w = act_in<XACT>(fmaf(v[i].w, isc.w, ish.w));
-      if (r0 + i * M::RSTEP >= rows_valid) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // rows past M stay zero (statistics)
+      va[i].x = act_in<XACT>(fmaf(va[i].x, sa.x, ha.x)); va[i].y = act_in<XACT>(fmaf(va[i].y, sa.y, ha.y));
+      va[i].z = act_in<XACT>(fmaf(va[i].z, sa.z, ha.z)); va[i].w = act_in<XACT>(fmaf(va[i].w, sa.w, ha.w));
+      vb[i].x = act_in<XACT>(fmaf(vb[i].x, sb.x, hb.x)); vb[i].y = act_in<XACT>(fmaf(vb[i].y, sb.y, hb.y));
+      vb[i].z = act_in<XACT>(fmaf(vb[i].z, sb.z, hb.z)); vb[i].w = act_in<XACT>(fmaf(vb[i].w, sb.w, hb.w));
+      if (r0 + i * M::RSTEP >= rows_valid) { va[i] = make_float4(0.f, 0.f, 0.f, 0.f); vb[i] = va[i]; }   // rows past M stay zero
     }
   }
   if (gate != nullptr && k < K) {
+    const bool k2 = k + 4 < K;
+    const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
     if (rps >= BM) {
       // a 128-row tile touches at most two samples: both gate vectors are requested up front (L1/L2 hits) instead of
       // one dependent load per row
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + (size_t)b0 * K + k));
+      const float4* gp0 = reinterpret_cast<const float4*>(gate + (size_t)b0 * K + k);
       const bool two = off0 + rows_valid > rps;
-      const float4 g1 = two ? __ldg(reinterpret_cast<const float4*>(gate + (size_t)(b0 + 1) * K + k)) : g0;
+      const float4* gp1 = two ? reinterpret_cast<const float4*>(gate + (size_t)(b0 + 1) * K + k) : gp0;
+      const float4 g0a = __ldg(gp0), g0b = k2 ? __ldg(gp0 + 1) : one, g1a = __ldg(gp1), g1b = k2 ? __ldg(gp1 + 1) : one;
 #pragma unroll
       for (int i = 0; i < M::ROWS; ++i) {
-        const float4 g = (off0 + r0 + i * M::RSTEP >= rps) ? g1 : g0;
-        v[i].x *= g.x; v[i].y *= g.y; v[i].z *= g.z; v[i].w *= g.w;
+        const bool hi_b = off0 + r0 + i * M::RSTEP >= rps;
+        const float4 ga = hi_b ? g1a : g0a, gb = hi_b ? g1b : g0b;
+        va[i].x *= ga.x; va[i].y *= ga.y; va[i].z *= ga.z; va[i].w *= ga.w;
+        vb[i].x *= gb.x; vb[i].y *= gb.y; vb[i].z *= gb.z; vb[i].w *= gb.w;
       }
     } else {
 #pragma unroll
       for (int i = 0; i < M::ROWS; ++i) {
         const int r = r0 + i * M::RSTEP;
         if (r < rows_valid) {
-          const float4 g = __ldg(reinterpret_cast<const float4*>(gate + (size_t)((off0 + r) / rps + b0) * K + k));
-          v[i].x *= g.x; v[i].y *= g.y; v[i].z *= g.z; v[i].w *= g.w;
+          const float4* gp = reinterpret_cast<const float4*>(gate + (size_t)((off0 + r) / rps + b0) * K + k);
+          const float4 ga = __ldg(gp), gb = k2 ? __ldg(gp + 1) : one;
+          va[i].x *= ga.x; va[i].y *= ga.y; va[i].z *= ga.z; va[i].w *= ga.w;
+          vb[i].x *= gb.x; vb[i].y *= gb.y; vb[i].z *= gb.z; vb[i].w *= gb.w;
         }
       }
     }
   }
+  __syncwarp();                                   // every lane of the row has its inputs before anyone overwrites them
 #pragma unroll
   for (int i = 0; i < M::ROWS; ++i) {
-    float4 h, l;
-    split4(v[i], h, l);
-    *reinterpret_cast<float4*>(hi + off + i * M::STRIDE) = h;
-    *reinterpret_cast<float4*>(lo + off + i * M::STRIDE) = l;
+    uint4 h, l;
+    split8(va[i], vb[i], h, l);
+    *reinterpret_cast<uint4*>(tile + out_hi + i * M::STRIDE) = h;
+    *reinterpret_cast<uint4*>(tile + out_lo + i * M::STRIDE) = l;
   }
 }
 
-// weight tile [rows < BN]: row n scaled by the folded-BatchNorm scale of the epilogue (FOLD), split hi/lo
+// weight tile [rows < BN]: row n scaled by the folded-BatchNorm scale of the epilogue (FOLD), split hi/lo in place
 template <int LG, bool FOLD>
-__device__ __forceinline__ void fix_w(unsigned char* hi, unsigned char* lo, int ft, int BN, const float* scale, int n0, int N) {
+__device__ __forceinline__ void fix_w(unsigned char* tile, int ft, int BN, const float* scale, int n0, int N) {
   using M = FixMap<LG>;
-  const int c = ft & ((1 << LG) - 1), r0 = ft >> LG;
-  const uint32_t off = swz(r0, c);
-  float4 v[M::ROWS];
+  const int cp = ft & ((1 << LG) - 1), r0 = ft >> LG;
+  const uint32_t row_off = (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128);
+  const int x = r0 & 7;
+  const uint32_t in0 = row_off + (((2 * cp) ^ x) << 4), in1 = row_off + (((2 * cp + 1) ^ x) << 4);
+  const uint32_t out_hi = row_off + ((cp ^ x) << 4), out_lo = row_off + (((4 + cp) ^ x) << 4);
+  float4 va[M::ROWS], vb[M::ROWS];
   float sc[M::ROWS];
 #pragma unroll
   for (int i = 0; i < M::ROWS; ++i) {
     const int r = r0 + i * M::RSTEP;
-    v[i] = r < BN ? *reinterpret_cast<const float4*>(hi + off + i * M::STRIDE) : make_float4(0.f, 0.f, 0.f, 0.f);
-    sc[i] = (FOLD && r < BN && n0 + r < N) ? __ldg(scale + n0 + r) : 0.f;
+    const bool ok = r < BN;
+    va[i] = ok ? *reinterpret_cast<const float4*>(tile + in0 + i * M::STRIDE) : make_float4(0.f, 0.f, 0.f, 0.f);
+    vb[i] = ok ? *reinterpret_cast<const float4*>(tile + in1 + i * M::STRIDE) : make_float4(0.f, 0.f, 0.f, 0.f);
+    sc[i] = (FOLD && ok && n0 + r < N) ? __ldg(scale + n0 + r) : 0.f;
   }
+  __syncwarp();
 #pragma unroll
   for (int i = 0; i < M::ROWS; ++i) {
     const int r = r0 + i * M::RSTEP;
     if (r < BN) {
-      if (FOLD) { v[i].x *= sc[i]; v[i].y *= sc[i]; v[i].z *= sc[i]; v[i].w *= sc[i]; }
-      float4 h, l;
-      split4(v[i], h, l);
-      *reinterpret_cast<float4*>(hi + off + i * M::STRIDE) = h;
-      *reinterpret_cast<float4*>(lo + off + i * M::STRIDE) = l;
+      if (FOLD) {
+        va[i].x *= sc[i]; va[i].y *= sc[i]; va[i].z *= sc[i]; va[i].w *= sc[i];
+        vb[i].x *= sc[i]; vb[i].y *= sc[i]; vb[i].z *= sc[i]; vb[i].w *= sc[i];
+      }
+      uint4 h, l;
+      split8(va[i], vb[i], h, l);
+      *reinterpret_cast<uint4*>(tile + out_hi + i * M::STRIDE) = h;
+      *reinterpret_cast<uint4*>(tile + out_lo + i * M::STRIDE) = l;
     }
   }
 }
 
-__device__ __forceinline__ int chunk_lg(int krem) {          // log2 of the 16-byte chunks (rounded up to 2 / 4 / 8) of a k-block
-  const int nch = krem >= KB ? 8 : (krem + 3) >> 2;
-  return nch <= 2 ? 1 : (nch <= 4 ? 2 : 3);
+// log2 of the 8-element chunk pairs of a k-block that are converted, rounded up to 2 or 4: a K=16 MMA step reads two hi
+// chunks, so an odd pair count must still overwrite the (zero-filled) partner chunk -- it holds raw fp32 bits otherwise
+__device__ __forceinline__ int pair_lg(int krem) {
+  return krem > 16 ? 2 : 1;
 }
 
 // EPI : 0 raw output (+ statistics), 1 + shift, 2 + shift + ReLU, 3 + shift + Hardswish   (scale lives in W)
@@ -267,9 +299,13 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
   if (p.r_blocks > 0) {
     for (int i = threadIdx.x; i < 32 * 8; i += kThreads) {             // 32 rows x 8 chunks
       const int r = i >> 3, c = i & 7;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if ((r >> 2) == c) { if ((r & 3) == 0) v.x = 1.f; else if ((r & 3) == 1) v.y = 1.f; else if ((r & 3) == 2) v.z = 1.f; else v.w = 1.f; }
-      *reinterpret_cast<float4*>(s_ident + swz(r, c)) = v;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);                              // bf16 1.0 = 0x3F80 at element k = r of row r
+      if ((r >> 3) == c) {
+        const uint32_t one = (r & 1) ? 0x3F800000u : 0x00003F80u;
+        const int w = (r & 7) >> 1;
+        if (w == 0) v.x = one; else if (w == 1) v.y = one; else if (w == 2) v.z = one; else v.w = one;
+      }
+      *reinterpret_cast<uint4*>(s_ident + swz(r, c)) = v;
     }
   }
   if (XACT >= 0) {
@@ -308,7 +344,7 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
           if (!first) mbar_wait(bar_empty + 8 * s_prev, ph_prev);
           mbar_expect_tx(bar_wfull, (uint32_t)p.k_blocks * w_tile);
           for (int kb = 0; kb < p.k_blocks; ++kb)
-            tma_load_2d(&mapW, bar_wfull, smem_u32(s_w) + (uint32_t)kb * 2u * w_tile, kb * KB, n0);
+            tma_load_2d(&mapW, bar_wfull, smem_u32(s_w) + (uint32_t)kb * w_tile, kb * KB, n0);
           cur_nt = nt;
         }
         next_tile();
@@ -320,7 +356,7 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
           if (kb < p.k_blocks) {
             mbar_expect_tx(bar_full + 8 * s, A_TILE + (p.wres ? 0u : w_tile));
             tma_load_2d(&mapA, bar_full + 8 * s, dst, kb * KB, m0);
-            if (!p.wres) tma_load_2d(&mapW, bar_full + 8 * s, dst + 2 * A_TILE, kb * KB, n0);
+            if (!p.wres) tma_load_2d(&mapW, bar_full + 8 * s, dst + A_TILE, kb * KB, n0);
           } else {
             mbar_expect_tx(bar_full + 8 * s, A_TILE);
             tma_load_2d(&mapR, bar_full + 8 * s, dst, n0 + (kb - p.k_blocks) * KB, m0);
@@ -337,7 +373,7 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
   } else if (warp == kMmaWarp) {
     // ================================================================= MMA issuer (one thread)
     if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(BN), idesc_id = idesc_tf32(32);
+      const uint32_t idesc = idesc_bf16(BN), idesc_id = idesc_bf16(32);
       const uint64_t desc0 = umma_desc(0);                   // descriptor of address 0: add (address >> 4)
       const uint64_t ident = desc0 + (smem_u32(s_ident) >> 4);
       const uint64_t wres0 = desc0 + (smem_u32(s_w) >> 4);
@@ -356,28 +392,29 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
           TT_MARK(2)
           tc_fence_after();
           const uint32_t sa = stage_base + (uint32_t)s * p.stage_bytes;
-          const uint64_t a_hi = desc0 + (sa >> 4), a_lo = a_hi + (A_TILE >> 4);
+          // row = [hi: 32 bf16 | lo: 32 bf16]; one K=16 MMA step covers 32 bytes: hi steps at +0/+32 B, lo at +64/+96 B
+          const uint64_t a_hi = desc0 + (sa >> 4), a_lo = a_hi + 4;
           if (kb < p.k_blocks) {
-            const uint64_t w_hi = p.wres ? wres0 + (uint32_t)kb * 2u * w_tile16 : a_hi + (2 * A_TILE >> 4);
-            const uint64_t w_lo = w_hi + w_tile16;
+            const uint64_t w_hi = p.wres ? wres0 + (uint32_t)kb * w_tile16 : a_hi + (A_TILE >> 4);
+            const uint64_t w_lo = w_hi + 4;
             const int krem = p.K - kb * KB;
-            const int nk8 = krem >= KB ? KB / 8 : (krem + 7) >> 3;
+            const int nk16 = krem >= KB ? 2 : (krem + 15) >> 4;
 #pragma unroll
-            for (int k8 = 0; k8 < 4; ++k8) {
-              if (k8 < nk8) {
-                const uint64_t ko = (uint64_t)(k8 * 2);             // 8 tf32 = 32 bytes along K, in 16-byte units
-                mma_tf32(tmem_d, a_hi + ko, w_hi + ko, idesc, (kb | k8) ? 1u : 0u);
-                mma_tf32(tmem_d, a_lo + ko, w_hi + ko, idesc, 1u);
-                mma_tf32(tmem_d, a_hi + ko, w_lo + ko, idesc, 1u);
+            for (int j = 0; j < 2; ++j) {
+              if (j < nk16) {
+                const uint64_t ko = (uint64_t)(j * 2);              // 16 bf16 = 32 bytes along K, in 16-byte units
+                mma_bf16(tmem_d, a_hi + ko, w_hi + ko, idesc, (kb | j) ? 1u : 0u);
+                mma_bf16(tmem_d, a_lo + ko, w_hi + ko, idesc, 1u);
+                mma_bf16(tmem_d, a_hi + ko, w_lo + ko, idesc, 1u);
               }
             }
           } else {                 // residual block j: D[:, 32j .. 32j+31] += R_hi . I + R_lo . I
             const uint32_t tmem_r = tmem_d + (uint32_t)(kb - p.k_blocks) * 32u;
 #pragma unroll
-            for (int k8 = 0; k8 < 4; ++k8) {
-              const uint64_t ko = (uint64_t)(k8 * 2);
-              mma_tf32(tmem_r, a_hi + ko, ident + ko, idesc_id, 1u);
-              mma_tf32(tmem_r, a_lo + ko, ident + ko, idesc_id, 1u);
+            for (int j = 0; j < 2; ++j) {
+              const uint64_t ko = (uint64_t)(j * 2);
+              mma_bf16(tmem_r, a_hi + ko, ident + ko, idesc_id, 1u);
+              mma_bf16(tmem_r, a_lo + ko, ident + ko, idesc_id, 1u);
             }
           }
           tc_commit(bar_empty + 8 * s);
@@ -397,17 +434,14 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     int s = 0, cur_nt = -1;
     uint32_t ph = 0, wphase = 0;
     const bool fold = EPI != 0 && p.scale != nullptr;
-    auto do_fix_w = [&](unsigned char* w_hi, int kb, int n0) {
-      const int lg = chunk_lg(p.K - kb * KB);
-      unsigned char* w_lo = w_hi + w_tile;
+    auto do_fix_w = [&](unsigned char* w, int kb, int n0) {
+      const int lg = pair_lg(p.K - kb * KB);
       if (fold) {
-        if (lg == 3) fix_w<3, true>(w_hi, w_lo, ft, BN, p.scale, n0, p.N);
-        else if (lg == 2) fix_w<2, true>(w_hi, w_lo, ft, BN, p.scale, n0, p.N);
-        else fix_w<1, true>(w_hi, w_lo, ft, BN, p.scale, n0, p.N);
+        if (lg == 2) fix_w<2, true>(w, ft, BN, p.scale, n0, p.N);
+        else fix_w<1, true>(w, ft, BN, p.scale, n0, p.N);
       } else {
-        if (lg == 3) fix_w<3, false>(w_hi, w_lo, ft, BN, nullptr, n0, p.N);
-        else if (lg == 2) fix_w<2, false>(w_hi, w_lo, ft, BN, nullptr, n0, p.N);
-        else fix_w<1, false>(w_hi, w_lo, ft, BN, nullptr, n0, p.N);
+        if (lg == 2) fix_w<2, false>(w, ft, BN, nullptr, n0, p.N);
+        else fix_w<1, false>(w, ft, BN, nullptr, n0, p.N);
       }
     };
     TT_DECL
@@ -417,7 +451,7 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       if (p.wres && nt != cur_nt) {
         mbar_wait(bar_wfull, wphase);
         wphase ^= 1u;
-        for (int kb = 0; kb < p.k_blocks; ++kb) do_fix_w(s_w + (size_t)kb * 2 * w_tile, kb, n0);
+        for (int kb = 0; kb < p.k_blocks; ++kb) do_fix_w(s_w + (size_t)kb * w_tile, kb, n0);
         cur_nt = nt;
       }
       next_tile();
@@ -427,17 +461,15 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         TT_MARK(0)
         mbar_wait(bar_full + 8 * s, ph);
         TT_MARK(1)
-        unsigned char* a_hi = smem + (size_t)s * p.stage_bytes;
-        unsigned char* a_lo = a_hi + A_TILE;
+        unsigned char* tile = smem + (size_t)s * p.stage_bytes;
         if (kb >= p.k_blocks) {
-          fix_a<3, -1>(a_hi, a_lo, ft, BM, nullptr, nullptr, 0, nullptr, 0, 0, 1, 0);            // residual tile: plain split
+          fix_a<2, -1>(tile, ft, BM, nullptr, nullptr, 0, nullptr, 0, 0, 1, 0);                   // residual tile: plain split
         } else {
-          const int lg = chunk_lg(p.K - kb * KB);
-          const int k = kb * KB + (ft & ((1 << lg) - 1)) * 4;
-          if (lg == 3) fix_a<3, XACT>(a_hi, a_lo, ft, rows_valid, s_isc, s_ish, k, p.gate, off0, b0, p.rps, p.K);
-          else if (lg == 2) fix_a<2, XACT>(a_hi, a_lo, ft, rows_valid, s_isc, s_ish, k, p.gate, off0, b0, p.rps, p.K);
-          else fix_a<1, XACT>(a_hi, a_lo, ft, rows_valid, s_isc, s_ish, k, p.gate, off0, b0, p.rps, p.K);
-          if (!p.wres) do_fix_w(a_hi + 2 * A_TILE, kb, n0);
+          const int lg = pair_lg(p.K - kb * KB);
+          const int k = kb * KB + (ft & ((1 << lg) - 1)) * 8;
+          if (lg == 2) fix_a<2, XACT>(tile, ft, rows_valid, s_isc, s_ish, k, p.gate, off0, b0, p.rps, p.K);
+          else fix_a<1, XACT>(tile, ft, rows_valid, s_isc, s_ish, k, p.gate, off0, b0, p.rps, p.K);
+          if (!p.wres) do_fix_w(tile + A_TILE, kb, n0);
         }
         TT_MARK(2)
         fence_proxy_async();
@@ -614,22 +646,25 @@ int launch_tma(const void* A, const float* W, void* C, const void* R, TmaParams 
   // (single-thread TMA / MMA issue, fix-up, TMEM read-out) is then overlapped by a second, independent tile stream.
   // Needs resident weights and >= 2 stages; otherwise one CTA takes the whole SM.
   const size_t w_tile = (size_t)p.BN * 128;
-  const size_t w_res = (size_t)p.k_blocks * 2 * w_tile;
+  const size_t w_res = (size_t)p.k_blocks * w_tile;
   const size_t ident = p.r_blocks > 0 ? 4096 : 0;
   const size_t floats = (2 * (size_t)p.kpad + BN_MAX + 8 * BN_MAX) * 4;
   const size_t barsz = (3 * 8 + 17) * 8 + 16;
   auto fixed = [&](int bufs) { return ident + (size_t)bufs * 4 * STG_BYTES + floats + barsz + 1024 /*alignment slack*/; };
   int ctas = 1;
+  bool stream2 = false;
   p.stg_bufs = 2;
   const char* force = getenv("EAT_TMA_CTAS");
   const size_t half = (kSmemLimit - 2048) / 2;
   if (!(force && atoi(force) == 1)) {
     for (int bufs = 2; bufs >= 1 && ctas == 1; --bufs)
-      if (fixed(bufs) + w_res + 2 * (size_t)(2 * A_TILE) <= half) { ctas = 2; p.stg_bufs = bufs; }
+      if (fixed(bufs) + w_res + 3 * (size_t)A_TILE <= half) { ctas = 2; p.stg_bufs = bufs; }
+    // large K: stream the weight k-blocks with A (stage = A tile + W tile); two CTAs still fit with >= 2 stages each
+    if (ctas == 1 && fixed(2) + 2 * ((size_t)A_TILE + w_tile) <= half) { ctas = 2; p.stg_bufs = 2; stream2 = true; }
   }
   const size_t limit = ctas == 2 ? half : kSmemLimit;
-  p.wres = ctas == 2 ? 1 : ((fixed(2) + w_res + 3 * (size_t)(2 * A_TILE) <= kSmemLimit) ? 1 : 0);
-  p.stage_bytes = (uint32_t)(2 * A_TILE + (p.wres ? 0 : 2 * w_tile));
+  p.wres = ctas == 2 ? (stream2 ? 0 : 1) : ((fixed(2) + w_res + 4 * (size_t)A_TILE <= kSmemLimit) ? 1 : 0);
+  p.stage_bytes = (uint32_t)(A_TILE + (p.wres ? 0 : w_tile));
   const size_t avail = limit - fixed(p.stg_bufs) - (p.wres ? w_res : 0);
   p.stages = (int)(avail / p.stage_bytes);
   if (p.stages > 8) p.stages = 8;
