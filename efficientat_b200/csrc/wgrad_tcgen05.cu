@@ -10,6 +10,9 @@
 // Each CTA owns one (128 x KT) tile of dW and one slice of the M range, accumulates it in TMEM and adds it to
 // dW with vector atomics (dW is zeroed by the caller once per step).
 // fp32 operands are split hi/lo into bf16 pairs (3 MMAs), as in pw_tcgen05.cu.
+#include <cstdlib>
+#include <cstring>
+
 #include "tc_common.cuh"
 
 namespace {
@@ -320,6 +323,11 @@ int launch_wg(const WgParams& p0, cudaStream_t st) {
 
 }  // namespace
 
+static bool use_tma_wgrad() {       // fp32 storage: the TMA-fed kernel (wgrad_tma.cu) unless EAT_WG_IMPL=tc
+  static const bool v = [] { const char* e = getenv("EAT_WG_IMPL"); return e == nullptr || strcmp(e, "tc") != 0; }();
+  return v;
+}
+
 extern "C" int eat_pw_tc_wgrad(const void* G, int g_dtype, const void* A, int a_dtype, float* dW, float* db, long long M,
                                int N, int K, const float* in_scale, const float* in_shift, int in_act,
                                const float* gate, int rows_per_sample, cudaStream_t st) {
@@ -330,11 +338,15 @@ extern "C" int eat_pw_tc_wgrad(const void* G, int g_dtype, const void* A, int a_
   if (M >= (1ll << 31) - MB) { eat_set_error("pw_tc_wgrad: M too large"); return EAT_ERR_ARG; }
   if ((((uintptr_t)G) | ((uintptr_t)A) | ((uintptr_t)dW)) & 15) { eat_set_error("pw_tc_wgrad: operands must be 16-byte aligned"); return EAT_ERR_ARG; }
   if (K % 4 != 0) { eat_set_error("pw_tc_wgrad: K must be a multiple of 4"); return EAT_ERR_ARG; }
+  if (a_dtype == EAT_F32 && use_tma_wgrad() && getenv("EAT_WG_NARROW") == nullptr)
+    return eat_pw_tma_wgrad((const float*)G, (const float*)A, dW, M, N, K, in_scale, in_shift, in_act, gate, rows_per_sample, 0, st);
   if (a_dtype == EAT_F32 && gate == nullptr) {
     // narrowest layers (N*K <= 512, huge M): exact-fp32 CUDA-core kernel, see wgrad_narrow.cu for the measurements
     const int rc = wgrad_narrow_launch((const float*)G, (const float*)A, dW, M, N, K, in_scale, in_shift, in_act, st);
     if (rc != EAT_ERR_UNSUPPORTED) return rc;
   }
+  if (a_dtype == EAT_F32 && use_tma_wgrad())
+    return eat_pw_tma_wgrad((const float*)G, (const float*)A, dW, M, N, K, in_scale, in_shift, in_act, gate, rows_per_sample, 0, st);
   WgParams p;
   p.G = G; p.A = A; p.dW = dW; p.M = (int)M; p.N = N; p.K = K;
   p.xf = InXform{in_scale, in_shift, gate, in_act, rows_per_sample > 0 ? rows_per_sample : 1};
@@ -351,6 +363,8 @@ extern "C" int eat_pw_tc_wgrad_persample(const void* G, const void* A, int dtype
   if (K % 8 != 0 || N % 8 != 0) { eat_set_error("pw_tc_wgrad_persample: K and N must be multiples of 8"); return EAT_ERR_ARG; }
   if (rows_per_sample < 1 || M % rows_per_sample != 0) { eat_set_error("pw_tc_wgrad_persample: M must be B * rows_per_sample"); return EAT_ERR_ARG; }
   if (M >= (1ll << 31) - MB) { eat_set_error("pw_tc_wgrad_persample: M too large"); return EAT_ERR_ARG; }
+  if (dtype == EAT_F32 && use_tma_wgrad())
+    return eat_pw_tma_wgrad((const float*)G, (const float*)A, S, M, N, K, nullptr, nullptr, 0, nullptr, rows_per_sample, 1, st);
   WgParams p;
   p.G = G; p.A = A; p.dW = S; p.M = (int)M; p.N = N; p.K = K;
   p.xf = InXform{nullptr, nullptr, nullptr, 0, rows_per_sample};

@@ -210,6 +210,14 @@ int eat_pw_tc_wgrad(const void* G, int g_dtype, const void* A, int a_dtype, floa
                     int K, const float* in_scale, const float* in_shift, int in_act, const float* gate,
                     int rows_per_sample, cudaStream_t stream);
 
+/* fp32-storage successor of eat_pw_tc_wgrad, fed by TMA (cp.async.bulk.tensor boxes of G and X, bf16 hi/lo split in
+ * place on chip, MN-major UMMA, two CTAs per SM).  per_sample != 0: S[b] = G_b^T . X_b for DynamicConv (M = B *
+ * rows_per_sample, dW = S [B, N, K]).  eat_pw_tc_wgrad / eat_pw_tc_wgrad_persample forward fp32 launches here unless the
+ * environment says EAT_WG_IMPL=tc. */
+int eat_pw_tma_wgrad(const float* G, const float* X, float* dW, long long M, int N, int K, const float* in_scale,
+                     const float* in_shift, int in_act, const float* gate, int rows_per_sample, int per_sample,
+                     cudaStream_t stream);
+
 /* BatchNorm backward, pass 1: s1[c] += sum dy, s2[c] += sum dy*xhat with dy = g * act'(z*scale+shift),
  * g = gA * gate[b,c] + dpool[b,c] (gA / gate / dpool each optional).  z, gA: [B, P, C]. */
 int eat_bn_bwd_reduce(const void* gA, const float* gate, const float* dpool, const void* z, const float* scale,
