@@ -5,6 +5,9 @@
 //   apply  : dz = gamma*invstd * (dy - s1/M - xhat * s2/M)
 // where the upstream gradient may be composed on the fly, g = gA * gate[b,c] + dpool[b,c]
 // (squeeze-excitation gate and the gradient of a spatial mean), so those products are never stored.
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace {
@@ -73,6 +76,77 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(
       }
 #pragma unroll
       for (int k = 0; k < V; ++k) { atomicAdd(&smem[c0 + k], a1[k]); atomicAdd(&smem[C + c0 + k], a2[k]); }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kThreads) {
+    atomicAdd(s1 + c, (double)smem[c]);
+    atomicAdd(s2 + c, (double)smem[C + c]);
+  }
+}
+
+// Second generation of the reduce pass.  Same thread mapping (a thread owns one channel vector and strides over the
+// pixels of one sample) but: the activation and the composition of the upstream gradient are compile-time (ACT, GM),
+// only three per-channel constants live in the loop (invstd is applied once at the end), and FOUR pixels = eight
+// 16-byte loads are in flight per thread before the first use (the v1 kernel was latency bound at 33 % occupancy).
+// GM: 0 g = gA;  1 g = gA * gate[b,c] + dpool[b,c] (either may be absent);  2 g = dpool[b,c] only (no gA tensor).
+template <typename T, int ACT, int GM>
+__global__ void __launch_bounds__(kThreads, 3) bn_bwd_reduce2_kernel(
+    const T* __restrict__ gA, const float* __restrict__ gate, const float* __restrict__ dpool,
+    const T* __restrict__ z, BnCtx bn, int B, int P, int C, double* __restrict__ s1, double* __restrict__ s2) {
+  constexpr int V = Vec<T>::N;
+  constexpr int U = V == 4 ? 4 : 2;  // pixels per trip (64 bytes of loads per tensor in flight either way)
+  extern __shared__ float smem[];   // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += kThreads) smem[i] = 0.f;
+  __syncthreads();
+  const int cv = C / V;
+  const int tcv = cv < kThreads ? cv : kThreads;
+  const int ppb = kThreads / tcv;
+  const int slot = threadIdx.x / tcv;
+  const int b = blockIdx.y;
+  if (slot < ppb) {
+    for (int cvi = threadIdx.x % tcv; cvi < cv; cvi += tcv) {
+      const int c0 = cvi * V;
+      float sc[V], sh[V], mu[V], gt[V], dp[V], a1[V], a2[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        sc[k] = bn.scale[c0 + k]; sh[k] = bn.shift[c0 + k]; mu[k] = bn.mean[c0 + k];
+        gt[k] = (GM == 1 && gate != nullptr) ? gate[(size_t)b * C + c0 + k] : 1.f;
+        dp[k] = (GM != 0 && dpool != nullptr) ? dpool[(size_t)b * C + c0 + k] : 0.f;
+        a1[k] = 0.f; a2[k] = 0.f;
+      }
+      auto one = [&](const float (&zv)[V], const float (&gv)[V]) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          float g = GM == 0 ? gv[k] : (GM == 1 ? fmaf(gv[k], gt[k], dp[k]) : dp[k]);
+          if (ACT != EAT_ACT_NONE) g *= act_bwd(fmaf(zv[k], sc[k], sh[k]), ACT);
+          a1[k] += g;
+          a2[k] = fmaf(g, zv[k] - mu[k], a2[k]);
+        }
+      };
+      const size_t base = (size_t)b * P * C + c0;
+      const int step = gridDim.x * ppb;
+      int p = blockIdx.x * ppb + slot;
+      for (; p + (U - 1) * step < P; p += U * step) {
+        float zz[U][V], gg[U][V];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const size_t o = base + (size_t)(p + u * step) * C;
+          Vec<T>::load(z + o, zz[u]);
+          if (GM != 2) Vec<T>::load(gA + o, gg[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) one(zz[u], gg[u]);
+      }
+      for (; p < P; p += step) {
+        const size_t o = base + (size_t)p * C;
+        float z0[V], g0[V];
+        Vec<T>::load(z + o, z0);
+        if (GM != 2) Vec<T>::load(gA + o, g0);
+        one(z0, g0);
+      }
+#pragma unroll
+      for (int k = 0; k < V; ++k) { atomicAdd(&smem[c0 + k], a1[k]); atomicAdd(&smem[C + c0 + k], a2[k] * bn.invstd[c0 + k]); }
     }
   }
   __syncthreads();
@@ -438,8 +512,27 @@ int launch_bn_bwd_reduce(const void* gA, const float* gate, const float* dpool, 
                          int C, double* s1, double* s2, cudaStream_t st) {
   constexpr int V = Vec<T>::N;
   const int cv = C / V, tcv = cv < kThreads ? cv : kThreads, ppb = kThreads / tcv;
-  dim3 grid(grid2(P, ppb, B), B);
-  bn_bwd_reduce_kernel<T><<<grid, kThreads, 2 * C * sizeof(float), st>>>((const T*)gA, gate, dpool, (const T*)z, bn, B, P, C, s1, s2);
+  static const bool v1 = [] { const char* e = getenv("EAT_BN_REDUCE"); return e != nullptr && strcmp(e, "v1") == 0; }();
+  if (v1) {
+    dim3 grid(grid2(P, ppb, B), B);
+    bn_bwd_reduce_kernel<T><<<grid, kThreads, 2 * C * sizeof(float), st>>>((const T*)gA, gate, dpool, (const T*)z, bn, B, P, C, s1, s2);
+    EAT_CHECK_LAUNCH();
+    return EAT_OK;
+  }
+  // ~12 CTAs per SM in total (3 resident at a time), at least 4 pixels per thread
+  int gx = ceil_div(P, ppb * 4);
+  const int cap = max(1, (148 * 12) / max(B, 1));
+  if (gx > cap) gx = cap;
+  dim3 grid(gx < 1 ? 1 : gx, B);
+  const size_t sm = 2 * C * sizeof(float);
+  const int gm = gA == nullptr ? 2 : ((gate != nullptr || dpool != nullptr) ? 1 : 0);
+#define EAT_RED(ACT, GM) bn_bwd_reduce2_kernel<T, ACT, GM><<<grid, kThreads, sm, st>>>((const T*)gA, gate, dpool, (const T*)z, bn, B, P, C, s1, s2)
+#define EAT_RED_A(ACT) do { if (gm == 0) EAT_RED(ACT, 0); else if (gm == 1) EAT_RED(ACT, 1); else EAT_RED(ACT, 2); } while (0)
+  if (bn.act == EAT_ACT_RELU) EAT_RED_A(EAT_ACT_RELU);
+  else if (bn.act == EAT_ACT_HSWISH) EAT_RED_A(EAT_ACT_HSWISH);
+  else EAT_RED_A(EAT_ACT_NONE);
+#undef EAT_RED_A
+#undef EAT_RED
   EAT_CHECK_LAUNCH();
   return EAT_OK;
 }

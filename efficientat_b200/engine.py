@@ -403,6 +403,9 @@ class MNEngine:
         return t
 
     # ------------------------------------------------------------------ backward
+    def _block_modules(self):
+        return list(self.model.features)[1:-1]
+
     def param_list(self):
         return [p for p in self.model.parameters()]
 
@@ -495,8 +498,10 @@ class MNEngine:
             dy = da1
         return dy
 
-    def _backward(self, S, dlogits):
-        """-> dict {parameter: fp32 gradient view into one flat arena} (arena returned under key None)."""
+    def _backward(self, S, dlogits, on_ready=None):
+        """-> dict {parameter: fp32 gradient view into one flat arena} (arena returned under key None).
+        on_ready(flat, i): called after each stage with the index i of the first parameter (model.parameters() order)
+        whose gradient is final -- everything from i to the end is -- so a data-parallel trainer can start reducing."""
         L = lib()
         st = _stream()
         dev = dlogits.device
@@ -511,6 +516,11 @@ class MNEngine:
             G[p] = flat[off:off + p.numel()].view_as(p)
             off += p.numel()
         dlogits = dlogits.float().contiguous()
+        pidx = {id(p): i for i, p in enumerate(params)}
+
+        def done(module):
+            if on_ready is not None:
+                on_ready(flat, min(pidx[id(p)] for p in module.parameters()))
 
         # ---- classifier
         H = S["head"]
@@ -524,6 +534,7 @@ class MNEngine:
         self._wgrad(dpre, H["feat"], G[self.fc1.weight], G[self.fc1.bias], B, n1, cl, g_code=0, a_code=0)
         dfeat = torch.empty(B, cl, device=dev, dtype=torch.float32)
         self._gemm(dpre, self.fc1.weight, dfeat, B, cl, n1, a_code=0, c_code=0, w_trans=True)
+        done(self.fc1)
 
         # ---- last 1x1 conv (+BN+Hardswish, global average pool)
         Ls = S["last"]
@@ -534,10 +545,12 @@ class MNEngine:
         self._wgrad(dz, Ls["inp"], G[conv.weight], None, B * P, cl, conv.in_channels)
         dy = torch.empty_like(Ls["inp"])
         self._gemm(dz, conv.weight, dy, B * P, conv.in_channels, cl, w_trans=True)
+        done(self.last)
 
         # ---- blocks, last to first
-        for blk, R in zip(reversed(self.blocks), reversed(S["blocks"])):
+        for blk, R, mod in zip(reversed(self.blocks), reversed(S["blocks"]), reversed(self._block_modules())):
             dy = self._block_bwd(blk, R, dy, G, B)
+            done(mod)
         # ---- stem
         St = S["stem"]
         conv, bn = self.stem[0], self.stem[1]

@@ -41,6 +41,9 @@ class DyMNEngine(MNEngine):
         self.fc1, self.fc2 = m.classifier[2], m.classifier[5]
         self.dropout_p = m.classifier[4].p
 
+    def _block_modules(self):
+        return list(self.model.layers)
+
     def forward(self, x, return_fmaps=False):
         if not x.is_cuda:
             raise RuntimeError("efficientat_b200 models run on CUDA (sm_100a) only; got a CPU tensor")

@@ -54,6 +54,62 @@ def allreduce_mean_(flat, group=None):
     return flat
 
 
+class GradBucketer:
+    """Overlap of the gradient all-reduce with the backward pass (what DistributedDataParallel's buckets do for the
+    reference, ex_pl_audioset.py:287-293): the flat gradient arena (parameter order) is cut into `n_buckets` contiguous
+    ranges of roughly equal size; backward produces gradients from the LAST parameter to the first and reports
+    `ready(first_param_index)` after each stage, and every bucket whose parameters are all complete is sum-all-reduced
+    at once -- on a side CUDA stream for device tensors, so that it runs under the rest of backward (inside a CUDA graph
+    the fork / join becomes graph edges); synchronously for CPU tensors (gloo, test-suite).  `finish()` joins."""
+
+    def __init__(self, sizes, n_buckets=3, group=None):
+        self.group = group
+        self.offsets = [0]
+        for n in sizes:
+            self.offsets.append(self.offsets[-1] + int(n))
+        total = self.offsets[-1]
+        # bucket boundaries in PARAMETER indices, cut from the end (the classifier's gradients come first)
+        cuts, target, acc = [len(sizes)], total / max(1, n_buckets), 0
+        for i in range(len(sizes) - 1, 0, -1):
+            acc += int(sizes[i])
+            if acc >= target and len(cuts) < n_buckets:
+                cuts.append(i)
+                acc = 0
+        cuts.append(0)
+        self.bounds = sorted(set(cuts))                   # [0, ..., n_params]
+        self._side = None
+        self.reset()
+
+    def reset(self):
+        self._next = len(self.bounds) - 1                  # index of the upper bound of the next bucket to send
+
+    def _reduce(self, flat, lo, hi):
+        view = flat[self.offsets[lo]:self.offsets[hi]]
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return
+        if flat.is_cuda:
+            main = torch.cuda.current_stream(flat.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(flat.device)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+
+    def ready(self, flat, first_param_index):
+        """gradients of parameters >= first_param_index are final"""
+        while self._next > 0 and self.bounds[self._next - 1] >= first_param_index:
+            self._reduce(flat, self.bounds[self._next - 1], self.bounds[self._next])
+            self._next -= 1
+
+    def finish(self, flat):
+        self.ready(flat, 0)
+        if flat.is_cuda and self._side is not None:
+            torch.cuda.current_stream(flat.device).wait_stream(self._side)
+        self.reset()
+
+
 def broadcast_from_rank0_(flat, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.broadcast(flat, 0, group=group)

@@ -11,6 +11,7 @@ host RNG, as in the reference), the all-reduce and the Adam kernel stay eager.  
 host ~1 ms instead of ~45 ms, which is what keeps the GPU busy at small per-GPU batches."""
 import torch
 
+from . import parallel
 from ._lib import lib
 from .helpers.utils import mixup as draw_mixup
 
@@ -68,7 +69,7 @@ class AudioSetTrainer:
     `model.update_params(e)` (DyMN temperature schedule, ex_audioset.py:132-133)."""
 
     def __init__(self, model, mel, lr=8e-4, kd_lambda=0.1, mixup_alpha=0.3, weight_decay=0.0, adamw=False,
-                 betas=(0.9, 0.999), eps=1e-8, process_group=None, cuda_graph=False, schedule=None):
+                 betas=(0.9, 0.999), eps=1e-8, process_group=None, cuda_graph=False, schedule=None, grad_buckets=3):
         if not 0.0 <= kd_lambda <= 1.0:
             raise AssertionError("Lambda for Knowledge Distillation must be between 0 and 1.")     # ex_audioset.py:100
         self.model, self.mel = model, mel
@@ -82,6 +83,11 @@ class AudioSetTrainer:
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
         self._flatten()
+        # world > 1: the gradient all-reduce is cut into buckets that start on a side stream while backward is still
+        # running (parallel.GradBucketer); grad_buckets = 0 keeps one all-reduce after backward
+        self.bucketer = None
+        if self.world > 1 and grad_buckets and grad_buckets > 0:
+            self.bucketer = parallel.GradBucketer([p.numel() for p in self.engine.param_list()], grad_buckets, process_group)
         self.steps = 0
         self.cuda_graph = cuda_graph
         self._graphs = {}
@@ -124,9 +130,9 @@ class AudioSetTrainer:
         self.exp_avg = torch.zeros_like(flat)
         self.exp_avg_sq = torch.zeros_like(flat)
         if self.world > 1:
-            torch.distributed.broadcast(self.flat_p, 0, group=self.pg)
+            parallel.broadcast_from_rank0_(self.flat_p, group=self.pg)
             for b in self.model.buffers():
-                torch.distributed.broadcast(b, 0, group=self.pg)
+                parallel.broadcast_from_rank0_(b, group=self.pg)
 
     # ------------------------------------------------------------------ one step
     @staticmethod
@@ -185,7 +191,11 @@ class AudioSetTrainer:
                       known.data_ptr() if known is not None else 0,
                       perm_d.data_ptr() if perm_d is not None else 0, lam_d.data_ptr() if lam_d is not None else 0,
                       self.kd_lambda, B, logits.shape[1], dlogits.data_ptr(), loss_acc.data_ptr(), _stream())
-        grads = self.engine._backward(saved, dlogits)
+        if self.bucketer is not None:
+            grads = self.engine._backward(saved, dlogits, on_ready=self.bucketer.ready)
+            self.bucketer.finish(grads[None])                     # joins the side stream: the arena is reduced (sum)
+        else:
+            grads = self.engine._backward(saved, dlogits)
         return loss_acc, grads[None]
 
     def _graph_key(self, spec, y, teacher, perm_d, known):
@@ -235,7 +245,8 @@ class AudioSetTrainer:
             for b, sb in zip(self.model.buffers(), saved_buffers):
                 b.copy_(sb)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        # thread-local capture mode: the NCCL watchdog thread may touch the CUDA API while this thread captures
+        with torch.cuda.graph(graph, capture_error_mode="thread_local" if self.world > 1 else "global"):
             loss_acc, flat_g = self._core(st["spec"], st["y"], st["teacher"], st["perm"], st["lam"], st["known"])
         st.update(graph=graph, loss=loss_acc, grads=flat_g)
         return st
@@ -246,7 +257,7 @@ class AudioSetTrainer:
         self.engine.dropout_p = float(self.model.classifier[4].p)     # read at call time, not at engine construction
         with torch.cuda.device(self.flat_p.device):
             loss_acc, flat_g = self.forward_backward(wave, y, teacher, perm, lam, teacher_known)
-            if self.world > 1:
+            if self.world > 1 and self.bucketer is None:
                 torch.distributed.all_reduce(flat_g, group=self.pg)        # one collective per step (sum)
             self.steps += 1
             lib().adam_step(self.flat_p.data_ptr(), flat_g.data_ptr(), self.exp_avg.data_ptr(),
