@@ -291,9 +291,7 @@ def run_reference_gpu_arm(args):
                                "global_batch": args.batch * world, "parallelism": f"ddp{world}", "amp": args.amp},
                     "gpu_baseline": r, "clocks": clocks.summary()}
             print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    _shutdown(world)
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
@@ -597,10 +595,13 @@ def run_ours(args):
                                                  else "oracle port of the reference modules") + " on the host cores"}
     # ---- the reference's own GPU path on the same device(s): cuFFT / cuDNN / cuBLAS through the unmodified modules
     gb = None
+    import gc
+    if args.mode == "train":
+        real.close()                 # the captured graph holds NCCL kernels: it must die before the process group does
+        del real
+    del trainer, pf
+    gc.collect()
     if not args.no_gpu_baseline:
-        del trainer, pf
-        import gc
-        gc.collect()
         torch.cuda.empty_cache()
         gb = {}
         for amp in ("none", "bf16"):
@@ -610,9 +611,19 @@ def run_ours(args):
         if gb is not None:
             line["gpu_baseline"] = gb
         print(json.dumps(line), flush=True)
+    _shutdown(world)
+
+
+def _shutdown(world):
+    """leave a multi-rank run without giving NCCL's communicator teardown a chance to hang the launcher: every rank
+    passes a final barrier (the JSON line is out), then exits the process directly"""
     if world > 1:
+        import torch.distributed as dist
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -58,6 +58,33 @@ class _ZeroPool:
         return v
 
 
+class _Fork:
+    """Weight gradients are leaves of the backward graph: nothing downstream waits for them.  They are launched on a side
+    stream so that they run beside the data-gradient / BatchNorm chain of the same block (in a captured CUDA graph the
+    fork and join become graph edges): latency-bound tails of one kernel are filled by the other, and the two readers of
+    a gradient tensor (weight- and data-gradient GEMM) sweep it together, so its second read tends to hit L2.
+    Tensors the side stream reads are kept alive until `join`, after which the main stream may recycle them."""
+
+    def __init__(self, device, enabled):
+        self.enabled = enabled
+        self.side = torch.cuda.Stream(device) if enabled else None
+        self.keep = []
+
+    def run(self, fn, *tensors):
+        if not self.enabled:
+            fn()
+            return
+        self.side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side):
+            fn()
+        self.keep.extend(tensors)
+
+    def join(self):
+        if self.enabled:
+            torch.cuda.current_stream().wait_stream(self.side)
+            self.keep.clear()
+
+
 class MNEngine:
     def __init__(self, model):
         self.model = model
@@ -66,6 +93,10 @@ class MNEngine:
             raise ValueError(f"precision must be 'fp32' or 'bf16', got {self.precision}")
         self.gemm_impl = os.environ.get("EAT_GEMM", "auto")     # auto | simt (exact-fp32 CUDA cores everywhere)
         self.tc_min_rows = 1024                                  # tiny GEMMs (classifier, SE) stay on CUDA cores
+        # weight gradients on a side stream (see _Fork): measured +1.1 % at B=256 (36.6 vs 37.0 ms/step,
+        # profiles/README.md) -- both branches are HBM-bound -- so it stays an opt-in experiment
+        self.fork_wgrad = os.environ.get("EAT_FORK_WGRAD", "0") == "1"
+        self._fork = None
         self._se_scale = {}
         self._zero_pool = _ZeroPool()
         self._plan()
@@ -455,8 +486,9 @@ class MNEngine:
         # project: BN3 (no activation)
         dz3 = self._bn_bwd(dy, None, None, R["z3"], R["sc3"], R["sv3"], 0, B, Po, blk.cout,
                            G[blk.proj[1].weight], G[blk.proj[1].bias], dev)
-        self._wgrad(dz3, R["z2"], G[blk.proj[0].weight], None, B * Po, blk.cout, blk.cexp, in_sc=R["sc2"],
-                    in_act=blk.act, gate=gate, rows_per_sample=Po)
+        fork = self._fork if self._fork is not None else _Fork(dev, False)
+        fork.run(lambda: self._wgrad(dz3, R["z2"], G[blk.proj[0].weight], None, B * Po, blk.cout, blk.cexp, in_sc=R["sc2"],
+                                     in_act=blk.act, gate=gate, rows_per_sample=Po), dz3)
         dp = torch.empty_like(R["z2"])
         self._gemm(dz3, blk.proj[0].weight, dp, B * Po, blk.cexp, blk.cout, w_trans=True)
         dpool = None
@@ -471,17 +503,19 @@ class MNEngine:
             L.se_fc_bwd(dgate.data_ptr(), gate.data_ptr(), R["hidden"].data_ptr(), blk.se.fc1.weight.data_ptr(),
                         blk.se.fc2.weight.data_ptr(), 1.0 / Po, du2.data_ptr(), du1.data_ptr(), dpool.data_ptr(),
                         B, blk.cexp, Sq, st)
-            self._wgrad(du2, R["hidden"], G[blk.se.fc2.weight], G[blk.se.fc2.bias], B, blk.cexp, Sq, g_code=0, a_code=0)
-            self._wgrad(du1, R["mean"], G[blk.se.fc1.weight], G[blk.se.fc1.bias], B, Sq, blk.cexp, g_code=0, a_code=0)
+            fork.run(lambda: (self._wgrad(du2, R["hidden"], G[blk.se.fc2.weight], G[blk.se.fc2.bias], B, blk.cexp, Sq, g_code=0, a_code=0),
+                              self._wgrad(du1, R["mean"], G[blk.se.fc1.weight], G[blk.se.fc1.bias], B, Sq, blk.cexp, g_code=0, a_code=0)),
+                     du2, du1)
         # depthwise: BN2 + activation (+ SE gate / squeeze gradient composed on the fly)
         dz2 = self._bn_bwd(dp, gate, dpool, R["z2"], R["sc2"], R["sv2"], blk.act, B, Po, blk.cexp,
                            G[blk.dw[1].weight], G[blk.dw[1].bias], dev)
         has_exp = blk.expand is not None
         dw_in = R["z1"] if has_exp else R["inp"]
         sc1 = R["sc1"] if has_exp else None
-        L.dw_conv_wgrad(dz2.data_ptr(), dw_in.data_ptr(), _ptr(sc1[0]) if has_exp else 0,
-                        _ptr(sc1[1]) if has_exp else 0, blk.act if has_exp else 0, G[blk.dw[0].weight].data_ptr(),
-                        0, dc, B, Fi, Ti, blk.cexp, blk.k, blk.stride, st)
+        fork.run(lambda: L.dw_conv_wgrad(dz2.data_ptr(), dw_in.data_ptr(), _ptr(sc1[0]) if has_exp else 0,
+                                         _ptr(sc1[1]) if has_exp else 0, blk.act if has_exp else 0,
+                                         G[blk.dw[0].weight].data_ptr(), 0, dc, B, Fi, Ti, blk.cexp, blk.k, blk.stride,
+                                         _stream()), dz2)
         da1 = torch.empty_like(dw_in)
         # without an expand stage the depthwise input IS the block input: fold the residual gradient in
         L.dw_conv_dgrad(dz2.data_ptr(), R["wt"].data_ptr(), 0, _ptr(dy) if (blk.res and not has_exp) else 0,
@@ -489,7 +523,7 @@ class MNEngine:
         if has_exp:
             dz1 = self._bn_bwd(da1, None, None, R["z1"], R["sc1"], R["sv1"], blk.act, B, Pi, blk.cexp,
                                G[blk.expand[1].weight], G[blk.expand[1].bias], dev)
-            self._wgrad(dz1, R["inp"], G[blk.expand[0].weight], None, B * Pi, blk.cexp, blk.cin)
+            fork.run(lambda: self._wgrad(dz1, R["inp"], G[blk.expand[0].weight], None, B * Pi, blk.cexp, blk.cin), dz1)
             dinp = torch.empty_like(R["inp"])
             self._gemm(dz1, blk.expand[0].weight, dinp, B * Pi, blk.cin, blk.cexp, w_trans=True,
                        res=dy if blk.res else None)
@@ -516,22 +550,24 @@ class MNEngine:
             G[p] = flat[off:off + p.numel()].view_as(p)
             off += p.numel()
         dlogits = dlogits.float().contiguous()
+        fork = self._fork = _Fork(dev, self.fork_wgrad)
         pidx = {id(p): i for i, p in enumerate(params)}
 
         def done(module):
+            fork.join()                                  # this stage's weight gradients are complete
             if on_ready is not None:
                 on_ready(flat, min(pidx[id(p)] for p in module.parameters()))
 
         # ---- classifier
         H = S["head"]
         n1, ncls, cl = self.fc1.out_features, self.fc2.out_features, self.fc1.in_features
-        self._wgrad(dlogits, H["h_pre"], G[self.fc2.weight], G[self.fc2.bias], B, ncls, n1, in_sc=H["ident"], in_act=HS,
-                    gate=H["mask"], rows_per_sample=1, g_code=0, a_code=0)
+        fork.run(lambda: self._wgrad(dlogits, H["h_pre"], G[self.fc2.weight], G[self.fc2.bias], B, ncls, n1, in_sc=H["ident"],
+                                     in_act=HS, gate=H["mask"], rows_per_sample=1, g_code=0, a_code=0), dlogits)
         dh = torch.empty(B, n1, device=dev, dtype=torch.float32)
         self._gemm(dlogits, self.fc2.weight, dh, B, n1, ncls, a_code=0, c_code=0, w_trans=True)
         dpre = torch.empty_like(dh)
         L.act_bwd(dh.data_ptr(), H["h_pre"].data_ptr(), _ptr(H["mask"]), HS, dpre.data_ptr(), dh.numel(), st)
-        self._wgrad(dpre, H["feat"], G[self.fc1.weight], G[self.fc1.bias], B, n1, cl, g_code=0, a_code=0)
+        fork.run(lambda: self._wgrad(dpre, H["feat"], G[self.fc1.weight], G[self.fc1.bias], B, n1, cl, g_code=0, a_code=0), dpre)
         dfeat = torch.empty(B, cl, device=dev, dtype=torch.float32)
         self._gemm(dpre, self.fc1.weight, dfeat, B, cl, n1, a_code=0, c_code=0, w_trans=True)
         done(self.fc1)
@@ -542,7 +578,7 @@ class MNEngine:
         conv, bn = self.last[0], self.last[1]
         dpool = dfeat.mul_(1.0 / P)      # gradient of the spatial mean, broadcast inside the BN-backward kernels
         dz = self._bn_bwd(None, None, dpool, Ls["z"], Ls["sc"], Ls["sv"], HS, B, P, cl, G[bn.weight], G[bn.bias], dev)
-        self._wgrad(dz, Ls["inp"], G[conv.weight], None, B * P, cl, conv.in_channels)
+        fork.run(lambda: self._wgrad(dz, Ls["inp"], G[conv.weight], None, B * P, cl, conv.in_channels), dz)
         dy = torch.empty_like(Ls["inp"])
         self._gemm(dz, conv.weight, dy, B * P, conv.in_channels, cl, w_trans=True)
         done(self.last)
@@ -559,5 +595,7 @@ class MNEngine:
                            G[bn.bias], dev)
         L.stem_wgrad(dz0.data_ptr(), dc, S["x"].data_ptr(), G[conv.weight].data_ptr(), B, S["F"], S["T"], c0,
                      conv.stride[0], st)
+        fork.join()
+        self._fork = None
         G[None] = flat
         return G

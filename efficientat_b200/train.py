@@ -251,6 +251,16 @@ class AudioSetTrainer:
         st.update(graph=graph, loss=loss_acc, grads=flat_g)
         return st
 
+    def close(self):
+        """Drop the captured CUDA graph(s).  With world > 1 the graph holds NCCL kernels of the process group's
+        communicator: destroy the graph BEFORE `torch.distributed.destroy_process_group()`, which otherwise waits for it
+        forever (observed with NCCL 2.28)."""
+        self._graphs = {}
+        import gc
+        gc.collect()
+        if self.flat_p.is_cuda:
+            torch.cuda.synchronize(self.flat_p.device)
+
     def step(self, wave, y, teacher=None, perm=None, lam=None, teacher_known=None):
         self.model.train()
         self.mel.train()

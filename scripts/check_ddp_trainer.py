@@ -106,8 +106,12 @@ def main():
         out[f"ms_per_step_{name}"] = float(ms)
     if rank == 0:
         print(json.dumps(out), flush=True)
+    t.close()                         # graphs with NCCL kernels must be gone before the communicator is torn down
+    del t, m
     dist.barrier()
-    dist.destroy_process_group()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0)                       # (destroy_process_group() after graph-captured collectives was seen to hang at exit)
 
 
 if __name__ == "__main__":
