@@ -376,7 +376,7 @@ class KernelTimer:
             e0.record()
             fn(*args)
             e1.record()
-            self.records.append((name, e0, e1, algo_bytes(name, args)))
+            self.records.append((name, e0, e1, algo_bytes(name, args), args if name in ("eat_pw_tc_fwd", "eat_pw_tc_wgrad") else None))
         return call
 
     def __exit__(self, *a):
@@ -385,7 +385,7 @@ class KernelTimer:
 
     def table(self):
         agg = {}
-        for name, e0, e1, nbytes in self.records:
+        for name, e0, e1, nbytes, _ in self.records:
             ms = e0.elapsed_time(e1)
             t = agg.setdefault(name, [0.0, 0, 0, True])
             t[0] += ms
@@ -514,6 +514,13 @@ def run_ours(args):
     if use_graph:
         trainer.cuda_graph = True
     top_ms, top_n, top_bytes, bytes_ok = kt2.table()[top]
+    if os.environ.get("EAT_BENCH_KERNELS") == "2" and rank == 0:      # per-launch table of the GEMM entry points (last step)
+        per = len(kt2.records) // max(args.steps, 1)
+        for name, e0, e1, nbytes, a_ in kt2.records[-per:]:
+            if a_ is not None and name == "eat_pw_tc_fwd":
+                ms_ = e0.elapsed_time(e1)
+                print(f"  pw_fwd M={a_[6]:8d} N={a_[7]:4d} K={a_[8]:4d} xf={int(bool(a_[9]))} gate={int(bool(a_[12]))} res={int(bool(a_[17]))} "
+                      f"stats={int(bool(a_[18]))}  {ms_ * 1e3:8.1f} us {nbytes / ms_ / 1e6:7.0f} GB/s", file=sys.stderr)
 
     # ---- end to end: pinned host buffers -> H2D -> step -> D2H loss, every step.  The copies go through the package's
     # double-buffered HostPrefetcher (batch i+1 is copied on a side stream while step i runs, as a pinned-memory

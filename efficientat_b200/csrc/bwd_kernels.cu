@@ -493,6 +493,71 @@ __global__ void __launch_bounds__(kThreads) stem_wgrad_kernel(const T* __restric
   }
 }
 
+// Row-oriented stem weight gradient (fp32 dz, C <= 64): same walk as stem_row_kernel; the U = 4 gradient vectors and
+// the 36 input values of a trip are requested before the first use (the pixel-at-a-time kernel above had ONE 16-byte
+// load in flight per thread: 1 TB/s).
+template <int S>
+__global__ void __launch_bounds__(kThreads) stem_wgrad_row_kernel(const float* __restrict__ dz, const float* __restrict__ x,
+                                                                  float* __restrict__ dw, int B, int F, int Tn, int Fo,
+                                                                  int To, int C) {
+  constexpr int V = 4, U = 4;
+  __shared__ float s_acc[9 * 64];
+  for (int i = threadIdx.x; i < 9 * C; i += kThreads) s_acc[i] = 0.f;
+  __syncthreads();
+  const int cv = C / V;
+  const int ppb = kThreads / cv;
+  const int cvi = threadIdx.x % cv, slot = threadIdx.x / cv;
+  if (slot < ppb) {
+    float acc[9][V];
+#pragma unroll
+    for (int q = 0; q < 9; ++q)
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[q][k] = 0.f;
+    const int rows = B * Fo;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+      const int b = row / Fo, fo = row - b * Fo;
+      const float* xb = x + (size_t)b * F * Tn;
+      const float* grow = dz + (size_t)row * To * C + cvi * V;
+      const int f0 = fo * S - 1;
+      for (int to0 = slot; to0 < To; to0 += U * ppb) {
+        float4 g[U];
+        float xv[U][9];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int to = to0 + u * ppb, t0 = to * S - 1;
+          g[u] = to < To ? *reinterpret_cast<const float4*>(grow + (size_t)to * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const int f = f0 + ky;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const int t = t0 + kx;
+              xv[u][ky * 3 + kx] = (to < To && f >= 0 && f < F && t >= 0 && t < Tn) ? __ldg(xb + (size_t)f * Tn + t) : 0.f;
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float gv[V] = {g[u].x, g[u].y, g[u].z, g[u].w};
+#pragma unroll
+          for (int q = 0; q < 9; ++q)
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[q][k] = fmaf(gv[k], xv[u][q], acc[q][k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 9; ++q)
+#pragma unroll
+      for (int k = 0; k < V; ++k) atomicAdd(&s_acc[q * C + cvi * V + k], acc[q][k]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 9 * C; i += kThreads) {
+    const int q = i / C, c = i % C;
+    atomicAdd(dw + (size_t)c * 9 + q, s_acc[i]);
+  }
+}
+
 // head: dpre = dh * mask * act'(pre)   (fp32, [n])
 __global__ void act_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ pre,
                                const float* __restrict__ mask, int act, float* __restrict__ dpre, long long n) {
@@ -672,6 +737,14 @@ int eat_stem_wgrad(const void* dz, int dtype, const float* x, float* dw, int B, 
   if (npix == 0) return EAT_OK;
   if (npix >= (1ll << 31)) { eat_set_error("stem wgrad: B*Fo*To must be below 2^31"); return EAT_ERR_ARG; }
   const int ppb = kThreads / (C / V);
+  if (dtype == EAT_F32 && C <= 64 && (stride == 1 || stride == 2)) {
+    const int rows = B * Fo;
+    const int grid_r = rows < 148 * 6 ? rows : 148 * 6;
+    if (stride == 2) stem_wgrad_row_kernel<2><<<grid_r, kThreads, 0, st>>>((const float*)dz, x, dw, B, F, T, Fo, To, C);
+    else stem_wgrad_row_kernel<1><<<grid_r, kThreads, 0, st>>>((const float*)dz, x, dw, B, F, T, Fo, To, C);
+    EAT_CHECK_LAUNCH();
+    return EAT_OK;
+  }
   int grid = (int)min((long long)148 * 4, ceil_div_ll(npix, ppb * 8));
   if (grid < 1) grid = 1;
   size_t smem = (size_t)9 * C * sizeof(float);

@@ -113,6 +113,90 @@ __global__ void __launch_bounds__(kThreads) stem_kernel(
   }
 }
 
+// Row-oriented stem (fp32 output, C <= 64): a CTA walks output rows (b, fo); a thread owns one channel vector -- its nine
+// weight vectors live in registers -- and every (256 / cv)-th output column of the row.  No divisions per pixel, no
+// shared-memory weight reads, and U = 4 independent pixels per trip so that their 36 input loads overlap.
+template <int S>
+__global__ void __launch_bounds__(kThreads) stem_row_kernel(
+    const float* __restrict__ x, const float* __restrict__ w /*[C,1,3,3]*/, float* __restrict__ out,
+    int B, int F, int T, int Fo, int To, int C,
+    const float* __restrict__ scale, const float* __restrict__ shift, int act,
+    double* __restrict__ stat_sum, double* __restrict__ stat_sq) {
+  constexpr int V = 4, U = 4;
+  __shared__ float s_sum[2 * 64];
+  for (int i = threadIdx.x; i < 2 * C; i += kThreads) s_sum[i] = 0.f;
+  __syncthreads();
+  const int cv = C / V;
+  const int ppb = kThreads / cv;
+  const int cvi = threadIdx.x % cv, slot = threadIdx.x / cv;
+  const bool active = slot < ppb;
+  float wr[9][V], sc[V], sh[V], lsum[V], lsq[V];
+#pragma unroll
+  for (int q = 0; q < 9; ++q)
+#pragma unroll
+    for (int i = 0; i < V; ++i) wr[q][i] = w[(cvi * V + i) * 9 + q];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    sc[i] = scale != nullptr ? scale[cvi * V + i] : 1.f;
+    sh[i] = scale != nullptr ? shift[cvi * V + i] : 0.f;
+    lsum[i] = 0.f; lsq[i] = 0.f;
+  }
+  const int rows = B * Fo;
+  if (active) {
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+      const int b = row / Fo, fo = row - b * Fo;
+      const float* xb = x + (size_t)b * F * T;
+      float* orow = out + (size_t)row * To * C + cvi * V;
+      const int f0 = fo * S - 1;
+      for (int to0 = slot; to0 < To; to0 += U * ppb) {
+        float xv[U][9];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int to = to0 + u * ppb, t0 = to * S - 1;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const int f = f0 + ky;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const int t = t0 + kx;
+              xv[u][ky * 3 + kx] = (to < To && f >= 0 && f < F && t >= 0 && t < T) ? __ldg(xb + (size_t)f * T + t) : 0.f;
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int to = to0 + u * ppb;
+          if (to >= To) break;
+          float acc[V] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int q = 0; q < 9; ++q)
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[i] = fmaf(xv[u][q], wr[q][i], acc[i]);
+          if (scale != nullptr) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[i] = act_fwd(fmaf(acc[i], sc[i], sh[i]), act);
+          } else {
+#pragma unroll
+            for (int i = 0; i < V; ++i) { lsum[i] += acc[i]; lsq[i] = fmaf(acc[i], acc[i], lsq[i]); }
+          }
+          *reinterpret_cast<float4*>(orow + (size_t)to * C) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        }
+      }
+    }
+  }
+  if (stat_sum != nullptr) {
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) { atomicAdd(&s_sum[cvi * V + i], lsum[i]); atomicAdd(&s_sum[C + cvi * V + i], lsq[i]); }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+      atomicAdd(stat_sum + c, (double)s_sum[c]);
+      atomicAdd(stat_sq + c, (double)s_sum[C + c]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Depthwise k x k conv, pad (k-1)/2, stride S.  in [B, F, T, C] -> out [B, Fo, To, C].
 // wt: repacked weights [k*k][C] (flip != 0 reads them mirrored: the stride-1 data gradient is the same convolution
@@ -526,6 +610,14 @@ int eat_stem_fwd(const float* x, const float* w, void* out, int out_dtype, int B
   if (npix == 0) return EAT_OK;
   if (npix >= (1ll << 31)) { eat_set_error("stem: B*Fo*To must be below 2^31"); return EAT_ERR_ARG; }
   const int ppb = kThreads / (C / V);
+  if (out_dtype == EAT_F32 && C <= 64 && (stride == 1 || stride == 2)) {      // row-oriented kernel (every released width <= 4.0)
+    const int rows = B * Fo;
+    const int grid_r = rows < 148 * 8 ? rows : 148 * 8;
+    if (stride == 2) stem_row_kernel<2><<<grid_r, kThreads, 0, st>>>(x, w, (float*)out, B, F, T, Fo, To, C, scale, shift, act, stat_sum, stat_sq);
+    else stem_row_kernel<1><<<grid_r, kThreads, 0, st>>>(x, w, (float*)out, B, F, T, Fo, To, C, scale, shift, act, stat_sum, stat_sq);
+    EAT_CHECK_LAUNCH();
+    return EAT_OK;
+  }
   int grid = grid_for(npix, ppb, 148 * 8);
   size_t smem = (size_t)11 * C * sizeof(float);
   if (out_dtype == EAT_BF16)
