@@ -344,11 +344,11 @@ def algo_bytes(name, a):
 # DRAM traffic of the dominant kernel from one `ncu --set full` capture (profiles/README.md): dram read + write bytes
 # relative to the algorithmic bytes of the captured launch.  Used to scale the per-launch `traffic` figure.
 NCU_TRAFFIC = {
-    # `ncu --set full` capture of the training-forward launch M = 2 048 000, K = 16, N = 64 (ID 11 in the csv):
-    # dram__bytes_read 131.4 MB + dram__bytes_write 465.5 MB against 655.4 MB algorithmic (the tail of the output is
-    # still dirty in the 126 MB L2 when the kernel ends: no re-reads)
-    "eat_pw_tc_fwd": {"dram_bytes": 131.385e6 + 465.466112e6, "algorithmic_bytes": 2048000 * (16 + 64) * 4 + 64 * 16 * 4,
-                      "capture": "profiles/r01_ncu_full_final_kernels.csv"},
+    # `ncu --set full` capture (profiles/r02_ncu_full_pw_tma_wgrad_tma_mel.csv) of the data-gradient launch M = 2 048 000,
+    # K = 16, N = 64 of pw_tma_kernel at B = 64: dram read 131.2 MB + write 467.0 MB against 655.4 MB algorithmic (the tail
+    # of the output is still dirty in the 126 MB L2 when the kernel ends: no re-reads)
+    "eat_pw_tc_fwd": {"dram_bytes": 131.18336e6 + 466.999552e6, "algorithmic_bytes": 2048000 * (16 + 64) * 4 + 64 * 16 * 4,
+                      "capture": "profiles/r02_ncu_full_pw_tma_wgrad_tma_mel.csv"},
 }
 
 
@@ -586,8 +586,10 @@ def run_ours(args):
                          "traffic_source": NCU_TRAFFIC[top]["capture"] + " (dram/algorithmic ratio of the captured launch x "
                          "this run's algorithmic bytes per launch)" if top in NCU_TRAFFIC else None,
                          "peak_source": peak_src,
-                         "timing": "CUDA events around every launch of this kernel over the same K steps, launched eagerly right "
-                                   "after the graph-replayed timed region" if use_graph else "CUDA events inside the timed region",
+                         "timing": "CUDA events directly around every launch of this kernel over the same K steps, launched eagerly "
+                                   "right after the graph-replayed timed region with the stream parked behind a spin kernel "
+                                   "(the host runs ahead: no host gap inside an interval)" if use_graph
+                                   else "CUDA events inside the timed region",
                          "launches_timed": top_n, "avg_launch_ms": top_ms / max(top_n, 1),
                          "algorithmic_bytes_per_launch": top_bytes / max(top_n, 1) if bytes_ok else None},
             "kernel_time_shares": shares,

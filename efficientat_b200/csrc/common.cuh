@@ -118,6 +118,9 @@ int dw_dgrad2_slide_launch(const void* dz, const float* wt, long long wt_bstride
 int wgrad_narrow_launch(const float* G, const float* A, float* dW, long long M, int N, int K, const float* in_scale,
                         const float* in_shift, int in_act, cudaStream_t st);
 
+// C[M, N] = alpha * A[M, K] . W[K, N], fp32, 32 x 32 tiles (gemm_simt.cu)
+int gemm_small_kn_launch(const float* A, const float* W, float* C, int M, int N, int K, float alpha, cudaStream_t st);
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -187,7 +187,8 @@ int launch_gemm(const void* A, const float* W, int w_trans, void* C, long long M
 template <bool BT>
 __global__ void __launch_bounds__(256) gemm_small_kernel(
     const float* __restrict__ A, const float* __restrict__ W, float* __restrict__ C, int M, int N, int K, InXform xf,
-    const float* __restrict__ scale, const float* __restrict__ shift, int act, const float* __restrict__ residual) {
+    const float* __restrict__ scale, const float* __restrict__ shift, int act, const float* __restrict__ residual,
+    float alpha) {
   __shared__ float As[32][33];       // [row][k]
   __shared__ float Bs[32][36];       // [k][n], rows 16-byte aligned
   const int tid = threadIdx.x;
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(
   for (int j = 0; j < 4; ++j) {
     const int n = n0 + lc + j;
     if (n >= N) continue;
-    float v = acc[j];
+    float v = acc[j] * alpha;
     if (scale != nullptr) v *= __ldg(scale + n);
     if (shift != nullptr) v += __ldg(shift + n);
     v = act_fwd(v, act);
@@ -327,6 +328,15 @@ int launch_wgrad(const void* G, const void* A, float* dW, float* db, long long M
 
 }  // namespace
 
+// C[M, N] = alpha * A[M, K] . W[K, N]   (fp32, small M; used by the squeeze-excitation MLP backward, bwd_kernels.cu)
+int gemm_small_kn_launch(const float* A, const float* W, float* C, int M, int N, int K, float alpha, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(M, 32), (unsigned)ceil_div(N, 32));
+  InXform xf{nullptr, nullptr, nullptr, 0, 1};
+  gemm_small_kernel<true><<<grid, 256, 0, st>>>(A, W, C, M, N, K, xf, nullptr, nullptr, 0, nullptr, alpha);
+  EAT_CHECK_LAUNCH();
+  return EAT_OK;
+}
+
 extern "C" int eat_gemm_simt_fwd(const void* A, int a_dtype, const float* W, int w_trans, void* C, int c_dtype,
                                  long long M, int N, int K, const float* in_scale, const float* in_shift, int in_act,
                                  const float* gate, int rows_per_sample, const float* scale, const float* shift,
@@ -338,8 +348,8 @@ extern "C" int eat_gemm_simt_fwd(const void* A, int a_dtype, const float* W, int
   InXform xf{in_scale, in_shift, gate, in_act, rows_per_sample > 0 ? rows_per_sample : 1};
   if (a_dtype == EAT_F32 && c_dtype == EAT_F32 && M <= 1024 && stat_sum == nullptr) {
     dim3 grid((unsigned)ceil_div_ll(M, 32), (unsigned)ceil_div(N, 32));
-    if (w_trans) gemm_small_kernel<true><<<grid, 256, 0, st>>>((const float*)A, W, (float*)C, (int)M, N, K, xf, scale, shift, act, (const float*)residual);
-    else gemm_small_kernel<false><<<grid, 256, 0, st>>>((const float*)A, W, (float*)C, (int)M, N, K, xf, scale, shift, act, (const float*)residual);
+    if (w_trans) gemm_small_kernel<true><<<grid, 256, 0, st>>>((const float*)A, W, (float*)C, (int)M, N, K, xf, scale, shift, act, (const float*)residual, 1.f);
+    else gemm_small_kernel<false><<<grid, 256, 0, st>>>((const float*)A, W, (float*)C, (int)M, N, K, xf, scale, shift, act, (const float*)residual, 1.f);
     EAT_CHECK_LAUNCH();
     return EAT_OK;
   }
