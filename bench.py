@@ -302,6 +302,9 @@ def algo_bytes(name, a):
         A, adt, W, wt, C, cdt, M, N, K = a[:9]
         res = a[17]
         return M * K * sz(adt) + M * N * sz(cdt) * (2 if res else 1) + N * K * 4
+    if name == "eat_pw_tma_fwd":             # (A, W, w_trans, C, M, N, K, in_scale, in_shift, in_act, gate, rps, scale, shift, act, residual, ...)
+        M, N, K, res = a[4], a[5], a[6], a[15]
+        return M * K * 4 + M * N * 4 * (2 if res else 1) + N * K * 4
     if name == "eat_pw_tc_dyn_fwd":          # + the dyn_k weight banks (read once; re-reads per tile hit L2)
         A, dt, W, att, nk, C, M, N, K, rps = a[:10]
         res = a[16]
@@ -347,8 +350,8 @@ NCU_TRAFFIC = {
     # `ncu --set full` capture (profiles/r02_ncu_full_pw_tma_wgrad_tma_mel.csv) of the data-gradient launch M = 2 048 000,
     # K = 16, N = 64 of pw_tma_kernel at B = 64: dram read 131.2 MB + write 467.0 MB against 655.4 MB algorithmic (the tail
     # of the output is still dirty in the 126 MB L2 when the kernel ends: no re-reads)
-    "eat_pw_tc_fwd": {"dram_bytes": 131.18336e6 + 466.999552e6, "algorithmic_bytes": 2048000 * (16 + 64) * 4 + 64 * 16 * 4,
-                      "capture": "profiles/r02_ncu_full_pw_tma_wgrad_tma_mel.csv"},
+    "eat_pw_tma_fwd": {"dram_bytes": 131.18336e6 + 466.999552e6, "algorithmic_bytes": 2048000 * (16 + 64) * 4 + 64 * 16 * 4,
+                       "capture": "profiles/r02_ncu_full_pw_tma_wgrad_tma_mel.csv"},
 }
 
 
@@ -376,7 +379,7 @@ class KernelTimer:
             e0.record()
             fn(*args)
             e1.record()
-            self.records.append((name, e0, e1, algo_bytes(name, args), args if name in ("eat_pw_tc_fwd", "eat_pw_tc_wgrad") else None))
+            self.records.append((name, e0, e1, algo_bytes(name, args), args if name in ("eat_pw_tma_fwd", "eat_pw_tc_fwd", "eat_pw_tc_wgrad") else None))
         return call
 
     def __exit__(self, *a):
@@ -517,10 +520,10 @@ def run_ours(args):
     if os.environ.get("EAT_BENCH_KERNELS") == "2" and rank == 0:      # per-launch table of the GEMM entry points (last step)
         per = len(kt2.records) // max(args.steps, 1)
         for name, e0, e1, nbytes, a_ in kt2.records[-per:]:
-            if a_ is not None and name == "eat_pw_tc_fwd":
+            if a_ is not None and name == "eat_pw_tma_fwd":
                 ms_ = e0.elapsed_time(e1)
-                print(f"  pw_fwd M={a_[6]:8d} N={a_[7]:4d} K={a_[8]:4d} xf={int(bool(a_[9]))} gate={int(bool(a_[12]))} res={int(bool(a_[17]))} "
-                      f"stats={int(bool(a_[18]))}  {ms_ * 1e3:8.1f} us {nbytes / ms_ / 1e6:7.0f} GB/s", file=sys.stderr)
+                print(f"  pw_fwd M={a_[4]:8d} N={a_[5]:4d} K={a_[6]:4d} wT={a_[2]} xf={int(bool(a_[7]))} gate={int(bool(a_[10]))} "
+                      f"res={int(bool(a_[15]))} stats={int(bool(a_[16]))}  {ms_ * 1e3:8.1f} us {nbytes / ms_ / 1e6:7.0f} GB/s", file=sys.stderr)
 
     # ---- end to end: pinned host buffers -> H2D -> step -> D2H loss, every step.  The copies go through the package's
     # double-buffered HostPrefetcher (batch i+1 is copied on a side stream while step i runs, as a pinned-memory

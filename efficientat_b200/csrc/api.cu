@@ -12,7 +12,7 @@ void eat_set_error(const char* msg) {
 extern "C" {
 const char* eat_last_error(void) { return g_err; }
 // ABI version: bump when any signature in include/eat_b200.h changes.
-int eat_abi_version(void) { return 2; }
+int eat_abi_version(void) { return 3; }
 // 0 when a CUDA device of compute capability 10.x is visible, else an EAT_ERR_* code.
 int eat_device_check(int device) {
   cudaDeviceProp p;

@@ -644,8 +644,8 @@ extern "C" int eat_pw_tc_fwd(const void* A, int a_dtype, const float* W, int w_t
   if (a_dtype == EAT_F32 && !(residual != nullptr && act != EAT_ACT_NONE)) {
     static const bool use_tma = [] { const char* e = getenv("EAT_PW_IMPL"); return e == nullptr || strcmp(e, "tc") != 0; }();
     if (use_tma)     // fp32 storage: the TMA-fed TF32x3 kernel (pw_tma.cu)
-      return eat_pw_tma_fwd((const float*)A, W, (float*)C, M, N, K, in_scale, in_shift, in_act, gate, rows_per_sample, scale,
-                            shift, act, (const float*)residual, stat_sum, stat_sq, st);
+      return eat_pw_tma_fwd((const float*)A, W, 0, (float*)C, M, N, K, in_scale, in_shift, in_act, gate, rows_per_sample, scale,
+                            shift, act, (const float*)residual, stat_sum, stat_sq, nullptr, 0, st);
   }
   TcParams p;
   p.A = A; p.W = W; p.C = C; p.residual = residual; p.M = (int)M; p.N = N; p.K = K;

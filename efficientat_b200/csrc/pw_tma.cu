@@ -74,6 +74,7 @@ struct TmaParams {
   int stages, wres;                               // wres != 0: weight hi/lo tiles resident per N tile
   int n_acc, acc_cols, tmem_cols;                 // TMEM accumulators in flight (n_acc * acc_cols <= tmem_cols columns)
   int stg_bufs;                                   // staging buffers per epilogue warp (1 or 2)
+  int wpre;                                       // weights arrive pre-split (bf16 hi|lo rows, scale folded): no weight fix-up
   uint32_t stage_bytes, off_w, off_ident, off_stg, off_f, off_bar;   // shared-memory carve-up (bytes)
   int kpad;                                       // floats reserved for each of the in-transform vectors (0: none)
   const float* in_scale; const float* in_shift; const float* gate; int in_act; int rps;
@@ -177,7 +178,7 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
           if (!first) mbar_wait(bar_empty + 8 * s_prev, ph_prev);
           mbar_expect_tx(bar_wfull, (uint32_t)p.k_blocks * w_tile);
           for (int kb = 0; kb < p.k_blocks; ++kb)
-            tma_load_2d(&mapW, bar_wfull, smem_u32(s_w) + (uint32_t)kb * w_tile, kb * KB, n0);
+            tma_load_2d(&mapW, bar_wfull, smem_u32(s_w) + (uint32_t)kb * w_tile, kb * (p.wpre ? 2 * KB : KB), n0);
           cur_nt = nt;
         }
         next_tile();
@@ -189,7 +190,7 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
           if (kb < p.k_blocks) {
             mbar_expect_tx(bar_full + 8 * s, A_TILE + (p.wres ? 0u : w_tile));
             tma_load_2d(&mapA, bar_full + 8 * s, dst, kb * KB, m0);
-            if (!p.wres) tma_load_2d(&mapW, bar_full + 8 * s, dst + A_TILE, kb * KB, n0);
+            if (!p.wres) tma_load_2d(&mapW, bar_full + 8 * s, dst + A_TILE, kb * (p.wpre ? 2 * KB : KB), n0);
           } else {
             mbar_expect_tx(bar_full + 8 * s, A_TILE);
             tma_load_2d(&mapR, bar_full + 8 * s, dst, n0 + (kb - p.k_blocks) * KB, m0);
@@ -284,7 +285,8 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       if (p.wres && nt != cur_nt) {
         mbar_wait(bar_wfull, wphase);
         wphase ^= 1u;
-        for (int kb = 0; kb < p.k_blocks; ++kb) do_fix_w(s_w + (size_t)kb * w_tile, kb, n0);
+        if (!p.wpre)
+          for (int kb = 0; kb < p.k_blocks; ++kb) do_fix_w(s_w + (size_t)kb * w_tile, kb, n0);
         cur_nt = nt;
       }
       next_tile();
@@ -302,7 +304,7 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
           const int k = kb * KB + (ft & ((1 << lg) - 1)) * 8;
           if (lg == 2) fix_a<2, XACT>(tile, ft, rows_valid, s_isc, s_ish, k, p.gate, off0, b0, p.rps, p.K);
           else fix_a<1, XACT>(tile, ft, rows_valid, s_isc, s_ish, k, p.gate, off0, b0, p.rps, p.K);
-          if (!p.wres) do_fix_w(tile + A_TILE, kb, n0);
+          if (!p.wres && !p.wpre) do_fix_w(tile + A_TILE, kb, n0);
         }
         TT_MARK(2)
         fence_proxy_async();
@@ -428,10 +430,53 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------- host side
+// Weights pre-split once per launch: out[n][kb][64 bf16] = 32 hi | 32 lo values of W[n][32 kb ..] (x row_scale[n]), i.e. the
+// layout the in-kernel weight fix-up produces, so that the GEMM's TMA loads land finished operand tiles.  W is [N, K], or
+// [K, N] when `trans` (the data gradient uses the forward weight transposed; this replaces eat_transpose_f32 there).
+__global__ void w_split_kernel(const float* __restrict__ W, const float* __restrict__ row_scale, int trans,
+                               uint4* __restrict__ out, int N, int K, int k_blocks) {
+  const long long items = (long long)N * k_blocks * 4;             // one item = 8 consecutive k of one row
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+    const int cp = (int)(i & 3);
+    const long long t = i >> 2;
+    const int kb = (int)(t % k_blocks), n = (int)(t / k_blocks);
+    const int k0 = kb * KB + cp * 8;
+    float v[8];
+    const float sc = row_scale != nullptr ? __ldg(row_scale + n) : 1.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + j;
+      v[j] = k < K ? __ldg(trans ? W + (size_t)k * N + n : W + (size_t)n * K + k) * sc : 0.f;
+    }
+    uint4 hi, lo;
+    split8(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]), hi, lo);
+    uint4* row = out + ((size_t)n * k_blocks + kb) * 8;              // 8 chunks of 16 bytes per (row, k-block)
+    row[cp] = hi;
+    row[4 + cp] = lo;
+  }
+}
+
+// [rows, cols] bf16 row-major tensor, box = box_rows x 64 columns (128 bytes), SWIZZLE_128B
+int make_map_bf16(CUtensorMap* map, const void* ptr, long long rows, long long cols, int box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  if (enc == nullptr) { eat_set_error("pw_tma: cuTensorMapEncodeTiled is not available from this driver"); return EAT_ERR_CUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { eat_set_error("pw_tma: cuTensorMapEncodeTiled (bf16) failed"); return EAT_ERR_CUDA; }
+  return EAT_OK;
+}
+
 constexpr size_t kSmemLimit = 227 * 1024;
 
+struct WeightWs { int trans; void* ws; size_t bytes; };
+
 template <int EPI, int XACT>
-int launch_tma(const void* A, const float* W, void* C, const void* R, TmaParams p, cudaStream_t st) {
+int launch_tma(const void* A, const float* W, void* C, const void* R, TmaParams p, cudaStream_t st, WeightWs ws) {
   // ---- tiling
   if (p.N <= BN_MAX) { p.BN = ceil_div(p.N, 16) * 16; p.n_tiles = 1; }
   else {                                   // several N tiles: multiples of 32 so that no store chunk straddles two tiles
@@ -489,7 +534,21 @@ int launch_tma(const void* A, const float* W, void* C, const void* R, TmaParams 
   // ---- tensor maps
   CUtensorMap mA, mW, mC, mR;
   if (int rc = make_map(&mA, A, p.M, p.K, BM)) return rc;
-  if (int rc = make_map(&mW, W, p.N, p.K, p.BN)) return rc;
+  p.wpre = 0;
+  if (ws.ws != nullptr) {
+    // pre-split the weights (scale folded, optionally transposed) into the caller's workspace and read THAT through TMA
+    const size_t need = (size_t)p.N * p.k_blocks * 128;
+    if (ws.bytes < need || (((uintptr_t)ws.ws) & 127)) { eat_set_error("pw_tma: weight workspace too small or not 128-byte aligned"); return EAT_ERR_ARG; }
+    const long long items = (long long)p.N * p.k_blocks * 4;
+    const int grid = (int)min((long long)148 * 8, ceil_div_ll(items, 256));
+    w_split_kernel<<<grid, 256, 0, st>>>(W, (EPI != 0) ? p.scale : nullptr, ws.trans, reinterpret_cast<uint4*>(ws.ws), p.N, p.K, p.k_blocks);
+    EAT_CHECK_LAUNCH();
+    p.wpre = 1;
+    if (int rc = make_map_bf16(&mW, ws.ws, p.N, (long long)p.k_blocks * 64, p.BN)) return rc;
+  } else {
+    if (ws.trans) { eat_set_error("pw_tma: transposed weights need the weight workspace"); return EAT_ERR_ARG; }
+    if (int rc = make_map(&mW, W, p.N, p.K, p.BN)) return rc;
+  }
   if (int rc = make_map(&mC, C, p.M, p.N, 32)) return rc;
   if (int rc = make_map(&mR, R != nullptr ? R : C, p.M, p.N, BM)) return rc;
   static unsigned long long attr_mask = 0;
@@ -505,19 +564,19 @@ int launch_tma(const void* A, const float* W, void* C, const void* R, TmaParams 
 }
 
 template <int EPI>
-int launch_tma_x(const void* A, const float* W, void* C, const void* R, const TmaParams& p, cudaStream_t st) {
-  if (p.in_scale == nullptr) return launch_tma<EPI, -1>(A, W, C, R, p, st);
-  if (p.in_act == EAT_ACT_RELU) return launch_tma<EPI, 1>(A, W, C, R, p, st);
-  if (p.in_act == EAT_ACT_HSWISH) return launch_tma<EPI, 2>(A, W, C, R, p, st);
-  return launch_tma<EPI, 0>(A, W, C, R, p, st);
+int launch_tma_x(const void* A, const float* W, void* C, const void* R, const TmaParams& p, cudaStream_t st, WeightWs ws) {
+  if (p.in_scale == nullptr) return launch_tma<EPI, -1>(A, W, C, R, p, st, ws);
+  if (p.in_act == EAT_ACT_RELU) return launch_tma<EPI, 1>(A, W, C, R, p, st, ws);
+  if (p.in_act == EAT_ACT_HSWISH) return launch_tma<EPI, 2>(A, W, C, R, p, st, ws);
+  return launch_tma<EPI, 0>(A, W, C, R, p, st, ws);
 }
 
 }  // namespace
 
-extern "C" int eat_pw_tma_fwd(const float* A, const float* W, float* C, long long M, int N, int K, const float* in_scale,
-                              const float* in_shift, int in_act, const float* gate, int rows_per_sample,
-                              const float* scale, const float* shift, int act, const float* residual, double* stat_sum,
-                              double* stat_sq, cudaStream_t st) {
+extern "C" int eat_pw_tma_fwd(const float* A, const float* W, int w_trans, float* C, long long M, int N, int K,
+                              const float* in_scale, const float* in_shift, int in_act, const float* gate,
+                              int rows_per_sample, const float* scale, const float* shift, int act, const float* residual,
+                              double* stat_sum, double* stat_sq, void* w_ws, long long w_ws_bytes, cudaStream_t st) {
   if (M == 0) return EAT_OK;
   if (act == EAT_ACT_SIGMOID || in_act == EAT_ACT_SIGMOID) { eat_set_error("pw_tma: sigmoid epilogues run on the CUDA-core GEMM (eat_gemm_simt_fwd)"); return EAT_ERR_UNSUPPORTED; }
   const bool aff = scale != nullptr || shift != nullptr || act != 0;
@@ -534,8 +593,9 @@ extern "C" int eat_pw_tma_fwd(const float* A, const float* W, float* C, long lon
   p.M = (int)M; p.N = N; p.K = K;
   p.in_scale = in_scale; p.in_shift = in_shift; p.gate = gate; p.in_act = in_act; p.rps = rows_per_sample > 0 ? rows_per_sample : 1;
   p.scale = scale; p.shift = shift; p.stat_sum = stat_sum; p.stat_sq = stat_sq;
-  if (!aff) return launch_tma_x<0>(A, W, C, residual, p, st);
-  if (act == EAT_ACT_RELU) return launch_tma_x<2>(A, W, C, residual, p, st);
-  if (act == EAT_ACT_HSWISH) return launch_tma_x<3>(A, W, C, residual, p, st);
-  return launch_tma_x<1>(A, W, C, residual, p, st);
+  const WeightWs ws{w_trans, w_ws, (size_t)(w_ws_bytes > 0 ? w_ws_bytes : 0)};
+  if (!aff) return launch_tma_x<0>(A, W, C, residual, p, st, ws);
+  if (act == EAT_ACT_RELU) return launch_tma_x<2>(A, W, C, residual, p, st, ws);
+  if (act == EAT_ACT_HSWISH) return launch_tma_x<3>(A, W, C, residual, p, st, ws);
+  return launch_tma_x<1>(A, W, C, residual, p, st, ws);
 }

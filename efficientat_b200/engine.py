@@ -93,6 +93,7 @@ class MNEngine:
             raise ValueError(f"precision must be 'fp32' or 'bf16', got {self.precision}")
         self.gemm_impl = os.environ.get("EAT_GEMM", "auto")     # auto | simt (exact-fp32 CUDA cores everywhere)
         self.tc_min_rows = 1024                                  # tiny GEMMs (classifier, SE) stay on CUDA cores
+        self.pw_impl = "tc" if os.environ.get("EAT_PW_IMPL") == "tc" else "tma"
         # weight gradients on a side stream (see _Fork): measured +1.1 % at B=256 (36.6 vs 37.0 ms/step,
         # profiles/README.md) -- both branches are HBM-bound -- so it stays an opt-in experiment
         self.fork_wgrad = os.environ.get("EAT_FORK_WGRAD", "0") == "1"
@@ -157,7 +158,14 @@ class MNEngine:
         L = lib()
         use_tc = (self.gemm_impl != "simt" and a_code == c_code and M >= self.tc_min_rows and K % 8 == 0
                   and N % 8 == 0 and act != 3 and in_act != 3)      # sigmoid epilogues (DyMN context nets) stay on CUDA cores
-        if use_tc:
+        if use_tc and a_code == 0 and self.pw_impl == "tma" and not (res is not None and act != 0):
+            # fp32 storage: TMA-fed kernel; the weights are pre-split (bf16 hi|lo rows, BN scale folded, transposed for the
+            # data gradient) once per launch into this scratch, so no CTA repeats that per tile
+            ws = torch.empty(N * ((K + 31) // 32) * 128, device=w.device, dtype=torch.uint8)
+            L.pw_tma_fwd(a.data_ptr(), w.data_ptr(), 1 if w_trans else 0, out.data_ptr(), M, N, K, args[9], args[10], in_act,
+                         _ptr(gate), rows_per_sample, scale, shift, act, _ptr(res), args[18], args[19], ws.data_ptr(),
+                         ws.numel(), _stream())
+        elif use_tc:
             if w_trans:      # data gradient: feed W^T [N, K] as a K-major operand
                 wt = torch.empty(N, K, device=w.device, dtype=torch.float32)
                 L.transpose_f32(w.data_ptr(), wt.data_ptr(), K, N, _stream())

@@ -134,12 +134,15 @@ int eat_pw_tc_fwd(const void* A, int a_dtype, const float* W, int w_trans, void*
 /* fp32-storage version of the same contract, fed by TMA (cp.async.bulk.tensor tiles of A, W and the residual) with
  * TF32x3 products (hi/lo split on chip, ~2^-19 relative) and TMA stores; w_trans = 0, K and N multiples of 4.
  * The residual is accumulated before shift/activation, so residual != NULL requires act == EAT_ACT_NONE (the only
- * combination the reference has: block_types.py:167-171,179-180).  eat_pw_tc_fwd forwards fp32 launches here unless the
- * environment says EAT_PW_IMPL=tc. */
-int eat_pw_tma_fwd(const float* A, const float* W, float* C, long long M, int N, int K, const float* in_scale,
-                   const float* in_shift, int in_act, const float* gate, int rows_per_sample, const float* scale,
-                   const float* shift, int act, const float* residual, double* stat_sum, double* stat_sq,
-                   cudaStream_t stream);
+ * combination the reference has: block_types.py:167-171,179-180).  w_ws (optional, 128-byte aligned, at least
+ * N * ceil(K/32) * 128 bytes): scratch into which the weights are pre-split once per launch (bf16 hi|lo rows, epilogue
+ * scale folded, transposed when w_trans = 1, i.e. W given as [K, N]) so that no CTA repeats that work per tile; without
+ * it the split happens on chip per tile and w_trans must be 0.  eat_pw_tc_fwd forwards fp32 launches here (without
+ * workspace) unless the environment says EAT_PW_IMPL=tc. */
+int eat_pw_tma_fwd(const float* A, const float* W, int w_trans, float* C, long long M, int N, int K,
+                   const float* in_scale, const float* in_shift, int in_act, const float* gate, int rows_per_sample,
+                   const float* scale, const float* shift, int act, const float* residual, double* stat_sum,
+                   double* stat_sq, void* w_ws, long long w_ws_bytes, cudaStream_t stream);
 /* out[cols, rows] = in[rows, cols]^T (fp32); used to feed W^T to the data-gradient GEMM. */
 int eat_transpose_f32(const float* in, float* out, int rows, int cols, cudaStream_t stream);
 

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_string():
     l = _lib.lib()
-    assert l.abi_version() == 2
+    assert l.abi_version() == 3
     assert isinstance(l.last_error(), bytes)
 
 

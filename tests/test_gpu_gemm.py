@@ -82,6 +82,51 @@ def test_gemm_all_shapes_fused_epilogue(impl, dtype):
             assert ((stats[1] - q_ref).abs().max() / (q_ref.abs().max() + 1e-6)).item() < stol, (M, N, K)
 
 
+@pytest.mark.parametrize("w_trans", [0, 1])
+def test_tma_gemm_with_presplit_weights(w_trans):
+    """eat_pw_tma_fwd with the weight workspace (the engine's route): weights pre-split into bf16 hi|lo rows by a prep kernel
+    (epilogue scale folded; w_trans = 1: W handed over as [K, N], the data-gradient case), every variant / ragged shape."""
+    L = lib()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    st = torch.cuda.current_stream().cuda_stream
+    p = lambda t: 0 if t is None else t.data_ptr()
+    for idx, (M, N, K) in enumerate(SHAPES):
+        if K % 4 or N % 4:
+            continue
+        A = torch.randn(M, K, device="cuda", generator=g)
+        W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+        variant = idx % 4
+        in_sc = gate = sc = res = stats = None
+        in_act = act = 0
+        rps = 1
+        if variant in (1, 3):
+            in_sc = torch.stack([torch.rand(K, device="cuda", generator=g) + 0.5, torch.randn(K, device="cuda", generator=g) * 0.1])
+            in_act = 2 if variant == 1 else 1
+        if variant in (2, 3):
+            rps = 37
+            gate = torch.rand((M + rps - 1) // rps, K, device="cuda", generator=g)
+        if variant in (0, 2):
+            sc = torch.stack([torch.rand(N, device="cuda", generator=g) + 0.5, torch.randn(N, device="cuda", generator=g) * 0.1])
+            act = 2 if variant == 0 else 0
+            res = torch.randn(M, N, device="cuda", generator=g) if variant == 2 else None
+        else:
+            stats = torch.zeros(2, N, device="cuda", dtype=torch.float64)
+        C = torch.full((M, N), float("nan"), device="cuda")
+        Wg = W.t().contiguous() if w_trans else W
+        ws = torch.empty(N * ((K + 31) // 32) * 128, device="cuda", dtype=torch.uint8)
+        L.pw_tma_fwd(A.data_ptr(), Wg.data_ptr(), w_trans, C.data_ptr(), M, N, K, p(in_sc[0]) if in_sc is not None else 0,
+                     p(in_sc[1]) if in_sc is not None else 0, in_act, p(gate), rps, p(sc[0]) if sc is not None else 0,
+                     p(sc[1]) if sc is not None else 0, act, p(res), p(stats[0]) if stats is not None else 0,
+                     p(stats[1]) if stats is not None else 0, ws.data_ptr(), ws.numel(), st)
+        torch.cuda.synchronize()
+        ref, raw = _ref(A, W, in_sc, in_act, gate, rps, sc, act, res)
+        err = (C.double() - ref).abs().max().item() / (ref.abs().max().item() + 1e-6)
+        assert err < 2e-4, f"pw_tma_fwd(ws) w_trans={w_trans} shape {(M, N, K)} variant {variant}: rel err {err}"
+        if stats is not None:
+            s_ref = raw.sum(0)
+            assert ((stats[0] - s_ref).abs().max() / (s_ref.abs().max() + 1e-6)).item() < 1e-3, (M, N, K)
+
+
 def test_tc_gemm_large_streaming_shape():
     """block-2 expand of mn10 at B=32: M = 32*64*500 rows, K = 16 -> N = 64; checks the persistent tile loop."""
     M, N, K = 32 * 64 * 500, 64, 16
