@@ -3,10 +3,11 @@
 // normalised log-mel out.  Replaces reference models/preprocess.py:40-67 (eval path; the
 // fmin/fmax jitter of the training path only changes the filterbank table passed in).
 //
-// Work decomposition: grid = (ceil(T / 32), B).  A CTA owns 32 consecutive frames of one clip,
-// 256 threads = 4 groups of 64; each group transforms one frame at a time (512-point complex
-// FFT as three radix-8 Stockham passes, 8 complex values per thread in registers), 8 rounds.
-// Results are staged in shared memory as [n_mels][32] so the global store is 128 B per mel row.
+// Work decomposition: grid = (ceil(T / 16), B).  A CTA owns 16 consecutive frames of one clip: it stages its slice of the
+// pre-emphasised, reflect-padded signal in shared memory once (round 2; the frames overlap by n_fft - hop samples), then
+// 256 threads = 4 independent groups of 64 (group-local named barriers) transform one frame each per round (512-point
+// complex FFT as three radix-8 Stockham passes, 8 complex values per thread in registers), 4 rounds.
+// Results are staged in shared memory as [n_mels][16] so the global store is 64 B per mel row.
 // Algorithmic HBM bytes: 4*N read + 4*n_mels*T written per clip (1.792 MB at 10 s / 32 kHz).
 #include "common.cuh"
 #include "fft_core.cuh"
@@ -16,7 +17,7 @@ namespace {
 
 constexpr int kNfft = 1024;
 constexpr int kHalf = 512;          // complex FFT length
-constexpr int kFramesPerCta = 32;
+constexpr int kFramesPerCta = 16;
 constexpr int kGroups = 4;
 constexpr int kThreads = 256;
 
@@ -29,16 +30,23 @@ struct MelParams {
   const float* fb_w;     // [max_len][n_mels] taps, tap-major
   float* out;            // [B, n_mels, T]
   int B, N, T, n_mels, win_length, hop, max_len;
+  int seg_len;           // samples of the pre-emphasised, reflect-padded signal a CTA stages: (frames - 1) * hop + n_fft
   float preemph;         // 0.97
   float log_offset;      // 1e-5
   float out_add, out_div;   // (v + 4.5) / 5
 };
 
+// sample s of the pre-emphasised signal p (length L = N-1) extended by reflection (torch.stft center=True);
+// positions only frames beyond T would touch (double reflection) read as 0
 __device__ __forceinline__ float preemph_sample(const float* __restrict__ x, int s, int L, float c) {
-  // s indexes the pre-emphasised signal p (length L = N-1) extended by reflection (torch.stft center=True)
   int q = s < 0 ? -s : s;
   if (q >= L) q = 2 * (L - 1) - q;
+  if (q < 0 || q >= L) return 0.f;
   return __ldg(x + q + 1) - c * __ldg(x + q);
+}
+
+__device__ __forceinline__ void group_sync(int grp) {       // the four 64-thread groups work on different frames: no CTA barrier
+  asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory");
 }
 
 __global__ void __launch_bounds__(kThreads) mel_kernel(MelParams p) {
@@ -47,7 +55,8 @@ __global__ void __launch_bounds__(kThreads) mel_kernel(MelParams p) {
   float* s_win = reinterpret_cast<float*>(s_tw + 1024);               // 1024 floats  (4 KB) zero-padded window
   float2* s_fft = reinterpret_cast<float2*>(s_win + kNfft);           // kGroups * 512 float2 (16 KB)
   float* s_pow = reinterpret_cast<float*>(s_fft + kGroups * kHalf);   // kGroups * 516 floats
-  float* s_out = s_pow + kGroups * 516;                               // n_mels * 33 floats
+  float* s_out = s_pow + kGroups * 516;                               // n_mels * (kFramesPerCta + 1) floats
+  float* s_sig = s_out + p.n_mels * (kFramesPerCta + 1);              // seg_len floats: the CTA's slice of the signal
 
   const int tid = threadIdx.x;
   const int grp = tid >> 6;
@@ -63,6 +72,12 @@ __global__ void __launch_bounds__(kThreads) mel_kernel(MelParams p) {
     int wi = i - lp;
     s_win[i] = (wi >= 0 && wi < p.win_length) ? p.window[wi] : 0.f;
   }
+  // pre-emphasis + reflection once per sample (coalesced), instead of 32 scalar global loads per thread and frame:
+  // neighbouring frames overlap by n_fft - hop samples
+  {
+    const int s0 = t_base * p.hop - kHalf;
+    for (int i = tid; i < p.seg_len; i += kThreads) s_sig[i] = preemph_sample(x, s0 + i, L, p.preemph);
+  }
   __syncthreads();
 
   float2* zf = s_fft + grp * kHalf;
@@ -71,24 +86,21 @@ __global__ void __launch_bounds__(kThreads) mel_kernel(MelParams p) {
   for (int round = 0; round < kFramesPerCta / kGroups; ++round) {
     const int fl = round * kGroups + grp;     // frame index inside the CTA tile
     const int t = t_base + fl;
-    const bool live = t < p.T;
+    const bool live = t < p.T;                // uniform within a group
     float2 v[8];
-    // ---- pass 1 (Ns = 1): gather straight from global memory
+    // ---- pass 1 (Ns = 1): window the staged samples
     if (live) {
-      const int s0 = t * p.hop - kHalf;
+      const float* sg = s_sig + fl * p.hop;
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        int n = j + 64 * r;
-        float w0 = s_win[2 * n], w1 = s_win[2 * n + 1];
-        float a = (w0 != 0.f) ? w0 * preemph_sample(x, s0 + 2 * n, L, p.preemph) : 0.f;
-        float c = (w1 != 0.f) ? w1 * preemph_sample(x, s0 + 2 * n + 1, L, p.preemph) : 0.f;
-        v[r] = make_float2(a, c);
+        const int n = j + 64 * r;
+        v[r] = make_float2(s_win[2 * n] * sg[2 * n], s_win[2 * n + 1] * sg[2 * n + 1]);
       }
       stockham8_compute(v, j, 1, s_tw);
 #pragma unroll
       for (int r = 0; r < 8; ++r) zf[stockham8_dst(j, 1, r)] = v[r];
     }
-    __syncthreads();
+    group_sync(grp);
     // ---- pass 2 (Ns = 8), pass 3 (Ns = 64), in place with a barrier between gather and scatter
 #pragma unroll
     for (int Ns = 8; Ns <= 64; Ns *= 8) {
@@ -97,12 +109,12 @@ __global__ void __launch_bounds__(kThreads) mel_kernel(MelParams p) {
         for (int r = 0; r < 8; ++r) v[r] = zf[j + 64 * r];
         stockham8_compute(v, j, Ns, s_tw);
       }
-      __syncthreads();
+      group_sync(grp);
       if (live) {
 #pragma unroll
         for (int r = 0; r < 8; ++r) zf[stockham8_dst(j, Ns, r)] = v[r];
       }
-      __syncthreads();
+      group_sync(grp);
     }
     // ---- real-FFT split + power spectrum, bins 0..512
     if (live) {
@@ -114,24 +126,25 @@ __global__ void __launch_bounds__(kThreads) mel_kernel(MelParams p) {
       }
       if (j == 0) { float2 z0 = zf[0]; float nyq = z0.x - z0.y; pw[512] = nyq * nyq; }
     }
-    __syncthreads();
+    group_sync(grp);
     // ---- banded mel + log + affine into the staging tile
     if (live) {
       for (int m = j; m < p.n_mels; m += 64) {
         int st = __ldg(p.fb_start + m), len = __ldg(p.fb_len + m);
         float acc = 0.f;
         for (int i = 0; i < len; ++i) acc = fmaf(__ldg(p.fb_w + (size_t)i * p.n_mels + m), pw[st + i], acc);
-        s_out[m * 33 + fl] = (logf(acc + p.log_offset) + p.out_add) / p.out_div;
+        s_out[m * (kFramesPerCta + 1) + fl] = (logf(acc + p.log_offset) + p.out_add) / p.out_div;
       }
     }
-    // next round overwrites zf/pw only after the barrier at the end of its pass 1
+    group_sync(grp);                          // zf / pw are rewritten by this group's next round
   }
   __syncthreads();
-  // ---- coalesced store: each warp writes 32 consecutive frames of one mel row
+  // ---- store: 16 consecutive frames (64 bytes) of one mel row per half warp
   const int lane = tid & 31, warp = tid >> 5;
-  const int t = t_base + lane;
-  for (int m = warp; m < p.n_mels; m += kThreads / 32) {
-    if (t < p.T) p.out[((size_t)b * p.n_mels + m) * p.T + t] = s_out[m * 33 + lane];
+  const int fo = lane & (kFramesPerCta - 1), sub = lane / kFramesPerCta;       // two mel rows per warp instruction
+  const int t = t_base + fo;
+  for (int m = warp * 2 + sub; m < p.n_mels; m += (kThreads / 32) * 2) {
+    if (t < p.T) p.out[((size_t)b * p.n_mels + m) * p.T + t] = s_out[m * (kFramesPerCta + 1) + fo];
   }
 }
 
@@ -216,8 +229,11 @@ extern "C" int eat_mel_fwd(const float* wave, int B, int N, const float* window,
   p.fb_start = fb_start; p.fb_len = fb_len; p.fb_w = fb_w; p.out = out;
   p.B = B; p.N = N; p.T = 1 + (N - 1) / hop; p.n_mels = n_mels; p.win_length = win_length; p.hop = hop;
   p.max_len = max_len; p.preemph = preemph; p.log_offset = 1e-5f; p.out_add = 4.5f; p.out_div = 5.f;
+  p.seg_len = (kFramesPerCta - 1) * hop + kNfft;
   size_t smem = 1024 * sizeof(float2) + kNfft * sizeof(float) + kGroups * kHalf * sizeof(float2) +
-                kGroups * 516 * sizeof(float) + (size_t)n_mels * 33 * sizeof(float);
+                kGroups * 516 * sizeof(float) + (size_t)n_mels * (kFramesPerCta + 1) * sizeof(float) +
+                (size_t)p.seg_len * sizeof(float);
+  if (smem > 160 * 1024) { eat_set_error("eat_mel_fwd: hop too large for the shared-memory signal slice"); return EAT_ERR_UNSUPPORTED; }
   static unsigned long long attr_mask = 0;
   if (int rc = eat_opt_in_smem(mel_kernel, 160 * 1024, attr_mask)) return rc;
   dim3 grid(ceil_div(p.T, kFramesPerCta), B);
