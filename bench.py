@@ -305,6 +305,9 @@ def algo_bytes(name, a):
     if name == "eat_pw_tma_fwd":             # (A, W, w_trans, C, M, N, K, in_scale, in_shift, in_act, gate, rps, scale, shift, act, residual, ...)
         M, N, K, res = a[4], a[5], a[6], a[15]
         return M * K * 4 + M * N * 4 * (2 if res else 1) + N * K * 4
+    if name == "eat_pw_tma_dyn_fwd":         # (A, W, att, dyn_k, w_trans, C, M, N, K, rps, scale, shift, act, residual, ...)
+        nk, M, N, K, res = a[3], a[6], a[7], a[8], a[13]
+        return M * K * 4 + M * N * 4 * (2 if res else 1) + nk * N * K * 4
     if name == "eat_pw_tc_dyn_fwd":          # + the dyn_k weight banks (read once; re-reads per tile hit L2)
         A, dt, W, att, nk, C, M, N, K, rps = a[:10]
         res = a[16]

@@ -315,24 +315,64 @@ __global__ void __launch_bounds__(256) ctx_pool_bwd_kernel(const float* __restri
 
 // DynamicConv weight/attention gradients from per-sample weight gradients S [B, n]:
 //   dW[k, i] += sum_b att[b,k] S[b,i]           datt[b,k] = sum_i S[b,i] W[k,i]
-__global__ void dyn_wgrad_mix_kernel(const float* __restrict__ S, const float* __restrict__ att, float* __restrict__ dW,
-                                     int B, long long n, int k) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int b = 0; b < B; ++b) {
-      const float sv = S[(size_t)b * n + i];
-      for (int j = 0; j < k; ++j) acc[j] = fmaf(att[(size_t)b * k + j], sv, acc[j]);
+// Both passes stream S (B * n floats: 315 MB for the widest dymn20 layer at B = 128) and were latency bound with one
+// 4-byte load in flight per thread (1.4 TB/s); now 16-byte loads, four samples / two positions in flight per thread.
+__global__ void __launch_bounds__(256) dyn_wgrad_mix_kernel(const float* __restrict__ S, const float* __restrict__ att,
+                                                            float* __restrict__ dW, int B, long long n, int k) {
+  extern __shared__ float s_att[];                     // [B][4]
+  for (int i = threadIdx.x; i < B * 4; i += 256) s_att[i] = (i & 3) < k ? att[(size_t)(i >> 2) * k + (i & 3)] : 0.f;
+  __syncthreads();
+  const long long n4 = n >> 2;                         // n is a multiple of 4 (N, K multiples of 4)
+  for (long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += (long long)gridDim.x * blockDim.x) {
+    float4 acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* Sp = reinterpret_cast<const float4*>(S) + i4;
+    int b = 0;
+    for (; b + 3 < B; b += 4) {
+      float4 sv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) sv[u] = __ldg(Sp + (size_t)(b + u) * n4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a = s_att[(b + u) * 4 + j];
+          acc[j].x = fmaf(a, sv[u].x, acc[j].x); acc[j].y = fmaf(a, sv[u].y, acc[j].y);
+          acc[j].z = fmaf(a, sv[u].z, acc[j].z); acc[j].w = fmaf(a, sv[u].w, acc[j].w);
+        }
     }
-    for (int j = 0; j < k; ++j) dW[(size_t)j * n + i] += acc[j];
+    for (; b < B; ++b) {
+      const float4 sv = __ldg(Sp + (size_t)b * n4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = s_att[b * 4 + j];
+        acc[j].x = fmaf(a, sv.x, acc[j].x); acc[j].y = fmaf(a, sv.y, acc[j].y);
+        acc[j].z = fmaf(a, sv.z, acc[j].z); acc[j].w = fmaf(a, sv.w, acc[j].w);
+      }
+    }
+    for (int j = 0; j < k; ++j) {
+      float4* d = reinterpret_cast<float4*>(dW + (size_t)j * n) + i4;
+      float4 o = *d;
+      o.x += acc[j].x; o.y += acc[j].y; o.z += acc[j].z; o.w += acc[j].w;
+      *d = o;
+    }
   }
 }
+// grid (chunks, B): each CTA reduces one slice of sample b and adds its four partial sums to datt (zeroed by the launcher)
 __global__ void __launch_bounds__(256) dyn_datt_kernel(const float* __restrict__ S, const float* __restrict__ W,
                                                        float* __restrict__ datt, long long n, int k) {
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;
+  const long long n4 = n >> 2;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (long long i = threadIdx.x; i < n; i += 256) {
-    const float sv = S[(size_t)b * n + i];
-    for (int j = 0; j < k; ++j) acc[j] = fmaf(sv, __ldg(W + (size_t)j * n + i), acc[j]);
+  const float4* Sp = reinterpret_cast<const float4*>(S + (size_t)b * n);
+  for (long long i4 = (long long)blockIdx.x * 256 + threadIdx.x; i4 < n4; i4 += (long long)gridDim.x * 256) {
+    const float4 sv = __ldg(Sp + i4);
+    float4 wv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wv[j] = j < k ? __ldg(reinterpret_cast<const float4*>(W + (size_t)j * n) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] += sv.x * wv[j].x + sv.y * wv[j].y + sv.z * wv[j].z + sv.w * wv[j].w;
   }
   __shared__ float red[8][4];
   for (int j = 0; j < 4; ++j) acc[j] = warp_sum(acc[j]);
@@ -341,8 +381,12 @@ __global__ void __launch_bounds__(256) dyn_datt_kernel(const float* __restrict__
   if (threadIdx.x < k) {
     float s = 0.f;
     for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-    datt[(size_t)b * k + threadIdx.x] = s;
+    atomicAdd(datt + (size_t)b * k + threadIdx.x, s);
   }
+}
+__global__ void zero_kernel(float* __restrict__ p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.f;
 }
 
 }  // namespace
@@ -464,8 +508,14 @@ int eat_dyn_wgrad_mix(const float* S, const float* att, const float* W, float* d
                       cudaStream_t st) {
   if (B == 0 || n == 0) return EAT_OK;
   if (k < 1 || k > 4) { eat_set_error("dyn_wgrad_mix: 1..4 kernels supported"); return EAT_ERR_UNSUPPORTED; }
-  dyn_wgrad_mix_kernel<<<ew_grid(n), 256, 0, st>>>(S, att, dW, B, n, k);
-  dyn_datt_kernel<<<B, 256, 0, st>>>(S, W, datt, n, k);
+  if ((n & 3) != 0 || ((((uintptr_t)S) | ((uintptr_t)W) | ((uintptr_t)dW)) & 15)) { eat_set_error("dyn_wgrad_mix: n must be a multiple of 4 and the tensors 16-byte aligned"); return EAT_ERR_ARG; }
+  const long long n4 = n >> 2;
+  const int gmix = (int)min((long long)148 * 8, ceil_div_ll(n4, 256));
+  dyn_wgrad_mix_kernel<<<gmix, 256, (size_t)B * 4 * sizeof(float), st>>>(S, att, dW, B, n, k);
+  zero_kernel<<<ceil_div(B * k, 256), 256, 0, st>>>(datt, B * k);
+  int chunks = (int)min((long long)max(1, (148 * 8) / B), ceil_div_ll(n4, 256 * 4));
+  if (chunks < 1) chunks = 1;
+  dyn_datt_kernel<<<dim3(chunks, B), 256, 0, st>>>(S, W, datt, n, k);
   EAT_CHECK_LAUNCH();
   return EAT_OK;
 }

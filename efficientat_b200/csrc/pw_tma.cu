@@ -75,6 +75,9 @@ struct TmaParams {
   int n_acc, acc_cols, tmem_cols;                 // TMEM accumulators in flight (n_acc * acc_cols <= tmem_cols columns)
   int stg_bufs;                                   // staging buffers per epilogue warp (1 or 2)
   int wpre;                                       // weights arrive pre-split (bf16 hi|lo rows, scale folded): no weight fix-up
+  int n_samples, tps, tile_rps;                   // M = n_samples * tile_rps rows; tps M tiles per sample (tiles never straddle
+                                                  // samples; 1 sample = the whole matrix for ordinary layers)
+  int wdyn;                                       // per-sample weights (DynamicConv): the weight map's third coordinate is the sample
   uint32_t stage_bytes, off_w, off_ident, off_stg, off_f, off_bar;   // shared-memory carve-up (bytes)
   int kpad;                                       // floats reserved for each of the in-transform vectors (0: none)
   const float* in_scale; const float* in_shift; const float* gate; int in_act; int rps;
@@ -163,6 +166,8 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
   // tile walk without divisions (m fastest: a CTA stays on one N tile while it can)
   int nt = blockIdx.x / p.m_tiles, mt = blockIdx.x - nt * p.m_tiles;
   auto next_tile = [&]() { mt += gridDim.x; while (mt >= p.m_tiles) { mt -= p.m_tiles; ++nt; } };
+  // (sample, M tile inside the sample) of M tile `m`; one sample = no division on the ordinary path
+  auto split_tile = [&](int m, int& bs, int& jt) { if (p.n_samples == 1) { bs = 0; jt = m; } else { bs = m / p.tps; jt = m - bs * p.tps; } };
 
   if (warp == 0) {
     // ================================================================= TMA producer (one thread)
@@ -172,14 +177,18 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       bool first = true;
       TT_DECL
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int m0 = mt * BM, n0 = nt * BN;
-        if (p.wres && nt != cur_nt) {
+        int bs, jt;
+        split_tile(mt, bs, jt);
+        const int m0 = jt * BM, n0 = nt * BN;                    // m0: row inside the sample
+        const int wb = p.wdyn ? bs : 0;
+        const int wkey = nt * p.n_samples + wb;
+        if (p.wres && wkey != cur_nt) {
           // every MMA that reads the old weights has retired once the most recently filled stage was released
           if (!first) mbar_wait(bar_empty + 8 * s_prev, ph_prev);
           mbar_expect_tx(bar_wfull, (uint32_t)p.k_blocks * w_tile);
           for (int kb = 0; kb < p.k_blocks; ++kb)
-            tma_load_2d(&mapW, bar_wfull, smem_u32(s_w) + (uint32_t)kb * w_tile, kb * (p.wpre ? 2 * KB : KB), n0);
-          cur_nt = nt;
+            tma_load_3d(&mapW, bar_wfull, smem_u32(s_w) + (uint32_t)kb * w_tile, kb * (p.wpre ? 2 * KB : KB), n0, wb);
+          cur_nt = wkey;
         }
         next_tile();
         for (int kb = 0; kb < kb_total; ++kb) {
@@ -189,11 +198,11 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
           const uint32_t dst = stage_base + (uint32_t)s * p.stage_bytes;
           if (kb < p.k_blocks) {
             mbar_expect_tx(bar_full + 8 * s, A_TILE + (p.wres ? 0u : w_tile));
-            tma_load_2d(&mapA, bar_full + 8 * s, dst, kb * KB, m0);
-            if (!p.wres) tma_load_2d(&mapW, bar_full + 8 * s, dst + A_TILE, kb * (p.wpre ? 2 * KB : KB), n0);
+            tma_load_3d(&mapA, bar_full + 8 * s, dst, kb * KB, m0, bs);
+            if (!p.wres) tma_load_3d(&mapW, bar_full + 8 * s, dst + A_TILE, kb * (p.wpre ? 2 * KB : KB), n0, wb);
           } else {
             mbar_expect_tx(bar_full + 8 * s, A_TILE);
-            tma_load_2d(&mapR, bar_full + 8 * s, dst, n0 + (kb - p.k_blocks) * KB, m0);
+            tma_load_3d(&mapR, bar_full + 8 * s, dst, n0 + (kb - p.k_blocks) * KB, m0, bs);
           }
           TT_MARK(2)
           s_prev = s; ph_prev = ph; first = false;
@@ -280,18 +289,21 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     };
     TT_DECL
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int m0 = mt * BM, n0 = nt * BN;
-      const int rows_valid = min(BM, p.M - m0);
-      if (p.wres && nt != cur_nt) {
+      int bs, jt;
+      split_tile(mt, bs, jt);
+      const int n0 = nt * BN;
+      const int rows_valid = min(BM, p.tile_rps - jt * BM);
+      const int wkey = nt * p.n_samples + (p.wdyn ? bs : 0);
+      if (p.wres && wkey != cur_nt) {
         mbar_wait(bar_wfull, wphase);
         wphase ^= 1u;
         if (!p.wpre)
           for (int kb = 0; kb < p.k_blocks; ++kb) do_fix_w(s_w + (size_t)kb * w_tile, kb, n0);
-        cur_nt = nt;
+        cur_nt = wkey;
       }
       next_tile();
       int b0 = 0, off0 = 0;
-      if (p.gate != nullptr) { b0 = m0 / p.rps; off0 = m0 - b0 * p.rps; }
+      if (p.gate != nullptr) { const int m0 = bs * p.tile_rps + jt * BM; b0 = m0 / p.rps; off0 = m0 - b0 * p.rps; }
       for (int kb = 0; kb < kb_total; ++kb) {
         TT_MARK(0)
         mbar_wait(bar_full + 8 * s, ph);
@@ -343,7 +355,9 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       asm volatile("bar.sync 1, 128;" ::: "memory");
     };
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int m0 = mt * BM, n0 = nt * BN;
+      int bs, jt;
+      split_tile(mt, bs, jt);
+      const int m0 = jt * BM, n0 = nt * BN;                      // m0: row inside the sample
       if (nt != cur_nt) {
         if (do_stats && cur_nt >= 0) flush_stats(cur_nt);
         if (EPI != 0) {
@@ -360,7 +374,7 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_cols);
       const int row0 = m0 + q * 32;
-      const int rows_left = min(32, p.M - row0);              // <= 0: nothing of this warp's slab is inside M
+      const int rows_left = min(32, p.tile_rps - row0);       // <= 0: nothing of this warp's slab is inside the sample
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (c * 32 < BN && n0 + c * 32 < p.N) {
@@ -405,7 +419,7 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
           }
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0 && rows_left > 0) { tma_store_2d(&mapC, smem_u32(buf), n0 + c * 32, row0); tma_commit(); }
+          if (lane == 0 && rows_left > 0) { tma_store_3d(&mapC, smem_u32(buf), n0 + c * 32, row0, bs); tma_commit(); }
           TT_MARK(3)
         }
       }
@@ -456,6 +470,43 @@ __global__ void w_split_kernel(const float* __restrict__ W, const float* __restr
   }
 }
 
+// DynamicConv (reference models/dymn/dy_block.py:103-131): per-sample kernels W_b = sum_j att[b, j] * W_j, mixed in fp32 and
+// written pre-split like above: out[b][n][kb][64 bf16].  W holds dyn_k kernels [dyn_k][N][K] ([dyn_k][K][N] when `trans`).
+__global__ void w_mix_split_kernel(const float* __restrict__ W, const float* __restrict__ att, int dyn_k,
+                                   const float* __restrict__ row_scale, int trans, uint4* __restrict__ out, int B, int N,
+                                   int K, int k_blocks) {
+  const long long per = (long long)N * k_blocks * 4;
+  const long long items = per * B;
+  const size_t bank = (size_t)N * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per);
+    const long long r = i - (long long)b * per;
+    const int cp = (int)(r & 3);
+    const long long t = r >> 2;
+    const int kb = (int)(t % k_blocks), n = (int)(t / k_blocks);
+    const int k0 = kb * KB + cp * 8;
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < dyn_k; ++j) a[j] = __ldg(att + (size_t)b * dyn_k + j);
+    const float sc = row_scale != nullptr ? __ldg(row_scale + n) : 1.f;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = k0 + e;
+      float acc = 0.f;
+      if (k < K) {
+        const size_t off = trans ? (size_t)k * N + n : (size_t)n * K + k;
+        for (int j = 0; j < dyn_k; ++j) acc = fmaf(a[j], __ldg(W + j * bank + off), acc);
+      }
+      v[e] = acc * sc;
+    }
+    uint4 hi, lo;
+    split8(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]), hi, lo);
+    uint4* row = out + (((size_t)b * N + n) * k_blocks + kb) * 8;
+    row[cp] = hi;
+    row[4 + cp] = lo;
+  }
+}
+
 // [rows, cols] bf16 row-major tensor, box = box_rows x 64 columns (128 bytes), SWIZZLE_128B
 int make_map_bf16(CUtensorMap* map, const void* ptr, long long rows, long long cols, int box_rows) {
   EncodeTiledFn enc = encode_fn();
@@ -473,7 +524,7 @@ int make_map_bf16(CUtensorMap* map, const void* ptr, long long rows, long long c
 
 constexpr size_t kSmemLimit = 227 * 1024;
 
-struct WeightWs { int trans; void* ws; size_t bytes; };
+struct WeightWs { int trans; void* ws; size_t bytes; const float* att; int dyn_k; };   // att != nullptr: DynamicConv kernel mix
 
 template <int EPI, int XACT>
 int launch_tma(const void* A, const float* W, void* C, const void* R, TmaParams p, cudaStream_t st, WeightWs ws) {
@@ -484,7 +535,9 @@ int launch_tma(const void* A, const float* W, void* C, const void* R, TmaParams 
     for (int bn : {96, 64}) { const int pad = ceil_div(p.N, bn) * bn; if (pad < best_pad) { best = bn; best_pad = pad; } }
     p.BN = best; p.n_tiles = ceil_div(p.N, best);
   }
-  p.m_tiles = ceil_div(p.M, BM);
+  if (p.n_samples < 1) { p.n_samples = 1; p.tile_rps = p.M; }
+  p.tps = ceil_div(p.tile_rps, BM);
+  p.m_tiles = p.n_samples * p.tps;
   p.k_blocks = ceil_div(p.K, KB);
   p.r_blocks = R != nullptr ? ceil_div(min(p.BN, p.N), 32) : 0;
   p.kpad = XACT >= 0 ? p.k_blocks * KB : 0;
@@ -533,24 +586,34 @@ int launch_tma(const void* A, const float* W, void* C, const void* R, TmaParams 
   if (smem > limit) { eat_set_error("pw_tma: shared-memory carve-up exceeds its budget"); return EAT_ERR_UNSUPPORTED; }
   // ---- tensor maps
   CUtensorMap mA, mW, mC, mR;
-  if (int rc = make_map(&mA, A, p.M, p.K, BM)) return rc;
+  const long long ns = p.n_samples, rps = p.tile_rps;
+  if (int rc = make_map3(&mA, A, ns, rps, p.K, BM, 4)) return rc;
   p.wpre = 0;
+  p.wdyn = 0;
   if (ws.ws != nullptr) {
-    // pre-split the weights (scale folded, optionally transposed) into the caller's workspace and read THAT through TMA
-    const size_t need = (size_t)p.N * p.k_blocks * 128;
+    // pre-split the weights (scale folded, optionally transposed, per sample for DynamicConv) into the caller's workspace
+    // and read THAT through TMA
+    const long long wsamples = ws.att != nullptr ? ns : 1;
+    const size_t need = (size_t)wsamples * p.N * p.k_blocks * 128;
     if (ws.bytes < need || (((uintptr_t)ws.ws) & 127)) { eat_set_error("pw_tma: weight workspace too small or not 128-byte aligned"); return EAT_ERR_ARG; }
-    const long long items = (long long)p.N * p.k_blocks * 4;
+    const long long items = wsamples * p.N * p.k_blocks * 4;
     const int grid = (int)min((long long)148 * 8, ceil_div_ll(items, 256));
-    w_split_kernel<<<grid, 256, 0, st>>>(W, (EPI != 0) ? p.scale : nullptr, ws.trans, reinterpret_cast<uint4*>(ws.ws), p.N, p.K, p.k_blocks);
+    const float* fold = (EPI != 0) ? p.scale : nullptr;
+    if (ws.att != nullptr) {
+      w_mix_split_kernel<<<grid, 256, 0, st>>>(W, ws.att, ws.dyn_k, fold, ws.trans, reinterpret_cast<uint4*>(ws.ws), (int)ns, p.N, p.K, p.k_blocks);
+      p.wdyn = 1;
+    } else {
+      w_split_kernel<<<grid, 256, 0, st>>>(W, fold, ws.trans, reinterpret_cast<uint4*>(ws.ws), p.N, p.K, p.k_blocks);
+    }
     EAT_CHECK_LAUNCH();
     p.wpre = 1;
-    if (int rc = make_map_bf16(&mW, ws.ws, p.N, (long long)p.k_blocks * 64, p.BN)) return rc;
+    if (int rc = make_map3(&mW, ws.ws, wsamples, p.N, (long long)p.k_blocks * 64, p.BN, 2)) return rc;
   } else {
-    if (ws.trans) { eat_set_error("pw_tma: transposed weights need the weight workspace"); return EAT_ERR_ARG; }
-    if (int rc = make_map(&mW, W, p.N, p.K, p.BN)) return rc;
+    if (ws.trans || ws.att != nullptr) { eat_set_error("pw_tma: transposed / per-sample weights need the weight workspace"); return EAT_ERR_ARG; }
+    if (int rc = make_map3(&mW, W, 1, p.N, p.K, p.BN, 4)) return rc;
   }
-  if (int rc = make_map(&mC, C, p.M, p.N, 32)) return rc;
-  if (int rc = make_map(&mR, R != nullptr ? R : C, p.M, p.N, BM)) return rc;
+  if (int rc = make_map3(&mC, C, ns, rps, p.N, 32, 4)) return rc;
+  if (int rc = make_map3(&mR, R != nullptr ? R : C, ns, rps, p.N, BM, 4)) return rc;
   static unsigned long long attr_mask = 0;
   if (int rc = eat_opt_in_smem(pw_tma_kernel<EPI, XACT>, kSmemLimit, attr_mask)) return rc;
   int dev = 0, sms = 148;
@@ -593,7 +656,38 @@ extern "C" int eat_pw_tma_fwd(const float* A, const float* W, int w_trans, float
   p.M = (int)M; p.N = N; p.K = K;
   p.in_scale = in_scale; p.in_shift = in_shift; p.gate = gate; p.in_act = in_act; p.rps = rows_per_sample > 0 ? rows_per_sample : 1;
   p.scale = scale; p.shift = shift; p.stat_sum = stat_sum; p.stat_sq = stat_sq;
-  const WeightWs ws{w_trans, w_ws, (size_t)(w_ws_bytes > 0 ? w_ws_bytes : 0)};
+  const WeightWs ws{w_trans, w_ws, (size_t)(w_ws_bytes > 0 ? w_ws_bytes : 0), nullptr, 0};
+  if (!aff) return launch_tma_x<0>(A, W, C, residual, p, st, ws);
+  if (act == EAT_ACT_RELU) return launch_tma_x<2>(A, W, C, residual, p, st, ws);
+  if (act == EAT_ACT_HSWISH) return launch_tma_x<3>(A, W, C, residual, p, st, ws);
+  return launch_tma_x<1>(A, W, C, residual, p, st, ws);
+}
+
+// DynamicConv 1x1 (reference models/dymn/dy_block.py:103-131) on the TMA kernel: W holds dyn_k kernels [dyn_k][N][K]
+// ([dyn_k][K][N] with w_trans = 1, the data gradient); sample b uses sum_j att[b, j] * W[j], mixed and pre-split once per
+// launch into w_ws (B * N * ceil(K/32) * 128 bytes).  M = B * rows_per_sample; tiles, loads and stores never cross a
+// sample (3-D tensor maps).
+extern "C" int eat_pw_tma_dyn_fwd(const float* A, const float* W, const float* att, int dyn_k, int w_trans, float* C,
+                                  long long M, int N, int K, int rows_per_sample, const float* scale, const float* shift,
+                                  int act, const float* residual, double* stat_sum, double* stat_sq, void* w_ws,
+                                  long long w_ws_bytes, cudaStream_t st) {
+  if (M == 0) return EAT_OK;
+  if (dyn_k < 1 || dyn_k > 4) { eat_set_error("pw_tma_dyn: 1..4 kernels supported"); return EAT_ERR_UNSUPPORTED; }
+  if (rows_per_sample < 1 || M % rows_per_sample != 0) { eat_set_error("pw_tma_dyn: M must be B * rows_per_sample"); return EAT_ERR_ARG; }
+  if (act == EAT_ACT_SIGMOID) { eat_set_error("pw_tma_dyn: sigmoid epilogue is not offered"); return EAT_ERR_UNSUPPORTED; }
+  const bool aff = scale != nullptr || shift != nullptr || act != 0;
+  if (residual != nullptr && act != EAT_ACT_NONE) { eat_set_error("pw_tma_dyn: residual + activation is not offered"); return EAT_ERR_UNSUPPORTED; }
+  if (stat_sum != nullptr && (aff || residual != nullptr)) { eat_set_error("pw_tma_dyn: statistics come from the raw-output variant only"); return EAT_ERR_UNSUPPORTED; }
+  if (K % 4 != 0 || N % 4 != 0) { eat_set_error("pw_tma_dyn: K and N must be multiples of 4"); return EAT_ERR_ARG; }
+  if (M >= (1ll << 31) - BM) { eat_set_error("pw_tma_dyn: M too large"); return EAT_ERR_ARG; }
+  if (w_ws == nullptr || att == nullptr) { eat_set_error("pw_tma_dyn: attention weights and the weight workspace are required"); return EAT_ERR_ARG; }
+  if ((((uintptr_t)A) | ((uintptr_t)W) | ((uintptr_t)C) | ((uintptr_t)residual)) & 15) { eat_set_error("pw_tma_dyn: operands must be 16-byte aligned"); return EAT_ERR_ARG; }
+  TmaParams p{};
+  p.M = (int)M; p.N = N; p.K = K;
+  p.rps = 1;
+  p.scale = scale; p.shift = shift; p.stat_sum = stat_sum; p.stat_sq = stat_sq;
+  p.n_samples = (int)(M / rows_per_sample); p.tile_rps = rows_per_sample;
+  const WeightWs ws{w_trans, w_ws, (size_t)(w_ws_bytes > 0 ? w_ws_bytes : 0), att, dyn_k};
   if (!aff) return launch_tma_x<0>(A, W, C, residual, p, st, ws);
   if (act == EAT_ACT_RELU) return launch_tma_x<2>(A, W, C, residual, p, st, ws);
   if (act == EAT_ACT_HSWISH) return launch_tma_x<3>(A, W, C, residual, p, st, ws);

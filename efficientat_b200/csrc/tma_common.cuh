@@ -33,6 +33,17 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
+// 3-D variants: the third coordinate is the sample, so that boxes never cross a sample boundary (rows past the end of a
+// sample are zero-filled on load and clipped on store by the TMA unit)
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
@@ -212,6 +223,23 @@ inline int make_map(CUtensorMap* map, const void* ptr, long long rows, int cols,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { eat_set_error("pw_tma: cuTensorMapEncodeTiled failed (pointer / stride alignment?)"); return EAT_ERR_CUDA; }
+  return EAT_OK;
+}
+
+// [samples, rows, cols] row-major tensor viewed through a {128-byte, box_rows, 1} box, SWIZZLE_128B; elem_bytes 4 (fp32,
+// 32 columns per box) or 2 (bf16, 64 columns per box)
+inline int make_map3(CUtensorMap* map, const void* ptr, long long samples, long long rows, long long cols, int box_rows,
+                     int elem_bytes) {
+  EncodeTiledFn enc = encode_fn();
+  if (enc == nullptr) { eat_set_error("tma: cuTensorMapEncodeTiled is not available from this driver"); return EAT_ERR_CUDA; }
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)samples};
+  cuuint64_t gstride[2] = {(cuuint64_t)cols * elem_bytes, (cuuint64_t)rows * cols * elem_bytes};
+  cuuint32_t box[3] = {(cuuint32_t)(128 / elem_bytes), (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                   const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { eat_set_error("tma: cuTensorMapEncodeTiled (3-D) failed (pointer / stride alignment?)"); return EAT_ERR_CUDA; }
   return EAT_OK;
 }
 

@@ -41,6 +41,8 @@ class DyMNEngine(MNEngine):
         self.fc1, self.fc2 = m.classifier[2], m.classifier[5]
         self.dropout_p = m.classifier[4].p
 
+    dyn_tma_min_rps = int(__import__("os").environ.get("EAT_DYN_TMA_MIN_RPS", "400"))     # measured: dymn20 B=128 1439 / 1513 / 1534 clips/s for inf / 1000 / 400
+
     def _block_modules(self):
         return list(self.model.layers)
 
@@ -78,6 +80,17 @@ class DyMNEngine(MNEngine):
         independent implementation the tensor-core path is checked against."""
         L = lib()
         dc = self.dcode
+        if (self.gemm_impl != "simt" and dc == 0 and self.pw_impl == "tma" and rps >= self.dyn_tma_min_rps
+                and not (res is not None and act != 0)):
+            # fp32 storage, many rows per sample: the TMA kernel; per-sample kernels mixed + pre-split once per launch into
+            # this scratch.  With few rows per sample the per-sample kernels (B * N * K floats through HBM) outweigh the
+            # activations and the register-staged kernel, which mixes the L2-resident banks on the fly, is the better fit
+            ws = torch.empty((M // rps) * N * ((K + 31) // 32) * 128, device=A.device, dtype=torch.uint8)
+            L.pw_tma_dyn_fwd(A.data_ptr(), W.data_ptr(), att.data_ptr(), nk, 0, C.data_ptr(), M, N, K, rps,
+                             _ptr(sc[0]) if sc is not None else 0, _ptr(sc[1]) if sc is not None else 0, act, _ptr(res),
+                             _ptr(stats[0]) if stats is not None else 0, _ptr(stats[1]) if stats is not None else 0,
+                             ws.data_ptr(), ws.numel(), _stream())
+            return
         if self.gemm_impl != "simt":
             L.pw_tc_dyn_fwd(A.data_ptr(), dc, W.data_ptr(), att.data_ptr(), nk, C.data_ptr(), M, N, K, rps, 0, 0, 0,
                             _ptr(sc[0]) if sc is not None else 0, _ptr(sc[1]) if sc is not None else 0, act, _ptr(res),
@@ -292,6 +305,17 @@ class DyMNEngine(MNEngine):
         W = conv.weight
         if self.gemm_impl == "simt":
             return self._dyn1x1_bwd_exact(conv, Gt, X, att, B, rps, N, K, G, res)
+        if dc == 0 and self.pw_impl == "tma" and rps >= self.dyn_tma_min_rps:
+            # data gradient dX_b = G_b . W_b: the same dynamic GEMM with the banks read transposed (no W^T copies)
+            dX = torch.empty(M, K, device=dev, dtype=self.tdtype)
+            ws = torch.empty(B * K * ((N + 31) // 32) * 128, device=dev, dtype=torch.uint8)
+            L.pw_tma_dyn_fwd(Gt.data_ptr(), W.data_ptr(), att.data_ptr(), nb, 1, dX.data_ptr(), M, K, N, rps, 0, 0, 0, _ptr(res),
+                             0, 0, ws.data_ptr(), ws.numel(), st)
+            S = torch.zeros(B, N * K, device=dev, dtype=torch.float32)             # per-sample weight gradients
+            L.pw_tc_wgrad_persample(Gt.data_ptr(), X.data_ptr(), dc, S.data_ptr(), M, N, K, rps, st)
+            datt = torch.empty(B, nb, device=dev, dtype=torch.float32)
+            L.dyn_wgrad_mix(S.data_ptr(), att.data_ptr(), W.data_ptr(), G[W].data_ptr(), datt.data_ptr(), B, N * K, nb, st)
+            return dX, datt
         Wt = torch.empty(nb, K, N, device=dev, dtype=torch.float32)           # W_k^T banks for the data gradient
         for j in range(nb):
             L.transpose_f32(W.data_ptr() + 4 * j * N * K, Wt.data_ptr() + 4 * j * N * K, N, K, st)

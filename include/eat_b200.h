@@ -143,6 +143,13 @@ int eat_pw_tma_fwd(const float* A, const float* W, int w_trans, float* C, long l
                    const float* in_scale, const float* in_shift, int in_act, const float* gate, int rows_per_sample,
                    const float* scale, const float* shift, int act, const float* residual, double* stat_sum,
                    double* stat_sq, void* w_ws, long long w_ws_bytes, cudaStream_t stream);
+/* DynamicConv 1x1 (models/dymn/dy_block.py:103-131) on the same TMA kernel: W = dyn_k kernels [dyn_k][N][K] ([dyn_k][K][N]
+ * with w_trans = 1), sample b uses sum_j att[b, j] * W[j]; the per-sample kernels are mixed + pre-split once per launch
+ * into w_ws (>= B * N * ceil(K/32) * 128 bytes, 128-byte aligned).  M = B * rows_per_sample. */
+int eat_pw_tma_dyn_fwd(const float* A, const float* W, const float* att, int dyn_k, int w_trans, float* C, long long M,
+                       int N, int K, int rows_per_sample, const float* scale, const float* shift, int act,
+                       const float* residual, double* stat_sum, double* stat_sq, void* w_ws, long long w_ws_bytes,
+                       cudaStream_t stream);
 /* out[cols, rows] = in[rows, cols]^T (fp32); used to feed W^T to the data-gradient GEMM. */
 int eat_transpose_f32(const float* in, float* out, int rows, int cols, cudaStream_t stream);
 

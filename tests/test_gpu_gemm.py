@@ -202,3 +202,54 @@ def test_tc_wgrad_matches_torch(dtype):
         err = ((dW.double() - ref).abs().max() / (ref.abs().max() + 1e-9)).item()
         tol = 2e-4 if dtype == torch.float32 else 2e-2
         assert err < tol, f"wgrad {dtype} {(M, N, K)} variant {variant}: rel err {err}"
+
+
+@pytest.mark.parametrize("w_trans", [0, 1])
+def test_tma_dynamic_gemm_matches_per_sample_reference(w_trans):
+    """eat_pw_tma_dyn_fwd (DynamicConv 1x1, dy_block.py:103-131): per-sample kernels sum_j att[b,j] W_j; tiles, loads and
+    stores never cross a sample (3-D tensor maps) -- rows per sample that are not multiples of 128 / 32, ragged N and K,
+    epilogue scale / shift / activation, residual, statistics; w_trans = 1 is the data-gradient orientation."""
+    L = lib()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    st = torch.cuda.current_stream().cuda_stream
+    p = lambda t: 0 if t is None else t.data_ptr()
+    for idx, (B, rps, N, K) in enumerate([(3, 500, 64, 16), (2, 2000, 24, 72), (5, 130, 200, 80), (4, 128, 112, 672), (2, 63, 8, 8),
+                                          (3, 504, 960, 160), (7, 37, 40, 120)]):
+        M, nk = B * rps, 4
+        A = torch.randn(M, K, device="cuda", generator=g)
+        W = torch.randn(nk, N, K, device="cuda", generator=g) / K ** 0.5
+        att = torch.softmax(torch.randn(B, nk, device="cuda", generator=g), 1)
+        variant = idx % 3
+        sc = res = stats = None
+        act = 0
+        if variant == 0:
+            stats = torch.zeros(2, N, device="cuda", dtype=torch.float64)
+        elif variant == 1:
+            sc = torch.stack([torch.rand(N, device="cuda", generator=g) + 0.5, torch.randn(N, device="cuda", generator=g) * 0.1])
+            act = 2
+        else:
+            sc = torch.stack([torch.rand(N, device="cuda", generator=g) + 0.5, torch.randn(N, device="cuda", generator=g) * 0.1])
+            res = torch.randn(M, N, device="cuda", generator=g)
+        Wg = W.transpose(1, 2).contiguous() if w_trans else W
+        C = torch.full((M, N), float("nan"), device="cuda")
+        ws = torch.empty(B * N * ((K + 31) // 32) * 128, device="cuda", dtype=torch.uint8)
+        L.pw_tma_dyn_fwd(A.data_ptr(), Wg.data_ptr(), att.data_ptr(), nk, w_trans, C.data_ptr(), M, N, K, rps,
+                         p(sc[0]) if sc is not None else 0, p(sc[1]) if sc is not None else 0, act, p(res),
+                         p(stats[0]) if stats is not None else 0, p(stats[1]) if stats is not None else 0, ws.data_ptr(),
+                         ws.numel(), st)
+        torch.cuda.synchronize()
+        Wb = torch.einsum("bj,jnk->bnk", att.double(), W.double())
+        raw = torch.einsum("brk,bnk->brn", A.double().view(B, rps, K), Wb).reshape(M, N)
+        ref = raw
+        if sc is not None:
+            ref = ref * sc[0].double() + sc[1].double()
+        if act == 2:
+            ref = torch.nn.functional.hardswish(ref)
+        if res is not None:
+            ref = ref + res.double()
+        err = (C.double() - ref).abs().max().item() / (ref.abs().max().item() + 1e-6)
+        assert err < 2e-4, f"pw_tma_dyn_fwd w_trans={w_trans} {(B, rps, N, K)} variant {variant}: rel err {err}"
+        if stats is not None:
+            s_ref, q_ref = raw.sum(0), (raw * raw).sum(0)
+            assert ((stats[0] - s_ref).abs().max() / (s_ref.abs().max() + 1e-6)).item() < 1e-3
+            assert ((stats[1] - q_ref).abs().max() / (q_ref.abs().max() + 1e-6)).item() < 1e-3
