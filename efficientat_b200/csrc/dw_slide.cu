@@ -24,6 +24,29 @@ namespace {
 constexpr int kST = 128;        // threads per CTA
 constexpr int kChMax = 512;     // channels per CTA (bounds the shared-memory weight table: 25 * 512 * 4 B = 50 KB)
 
+// c += a * b over a channel vector, two channels per instruction (FFMA2, sm_100: halves the issue slots of the tap loops;
+// each half is an ordinary IEEE fp32 fma, so results are bit-identical to fmaf)
+// PACK = false: scalar fmaf (the 3x3 stride-2 weight gradient spills with register pairs: 715 vs 465 us on the 64-channel
+// layer, profiles/r02_dw_ffma2_ab_microbench_b256.txt)
+template <int V, bool PACK = true>
+__device__ __forceinline__ void fma_vec(const float (&a)[V], const float (&b)[V], float (&c)[V]) {
+#ifdef EAT_DW_SCALAR_FMA          // A/B builds only (scripts/gpu_runs/r2_dwring2.sh)
+  constexpr bool kPack = false;
+#else
+  constexpr bool kPack = PACK;
+#endif
+  if constexpr (kPack) {
+#pragma unroll
+    for (int i = 0; i < V; i += 2) {
+      const float2 r = __ffma2_rn(make_float2(a[i], a[i + 1]), make_float2(b[i], b[i + 1]), make_float2(c[i], c[i + 1]));
+      c[i] = r.x; c[i + 1] = r.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; ++i) c[i] = fmaf(a[i], b[i], c[i]);
+  }
+}
+
 template <int XACT>
 __device__ __forceinline__ float xact(float v) {
   if (XACT == EAT_ACT_RELU) return fmaxf(v, 0.f);
@@ -31,6 +54,35 @@ __device__ __forceinline__ float xact(float v) {
   return v;
 }
 
+
+// Per-thread prefetch ring (cp.async): a thread's loads of the NEXT `depth` input rows are in flight while it multiplies
+// the current one.  Each thread reads back only what it copied itself, so cp.async.wait_group is the only synchronisation
+// (no CTA barrier); slot layout [depth][vectors][thread] keeps both the copies and the read-back conflict-free.
+template <int BYTES>
+__device__ __forceinline__ void cp_async(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_wait_pending(int n) {      // n = depth - 1 groups may stay in flight
+  switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+  }
+}
+constexpr int kRingMax = 6;
+// ring depth (<= maxd) that fits `budget` bytes of shared memory next to `fixed` bytes of tables; 0: ring off.
+// Measured (profiles/r02_dw_ring_microbench_b256.txt): two rows ahead is the sweet spot -- deeper rings take shared memory
+// away from the L1 that serves the column halo of neighbouring strips, and any ring that costs a resident CTA loses.
+inline int ring_depth(size_t budget, size_t fixed, size_t slot_bytes, int maxd) {
+  if (const char* e = getenv("EAT_DW_RING")) { const int v = atoi(e); if (v <= 0) return 0; if (v <= kRingMax) { return (fixed + v * slot_bytes <= 200 * 1024) ? v : 0; } }
+  if (maxd < 2 || budget <= fixed) return 0;
+  const size_t d = (budget - fixed) / slot_bytes;
+  return d >= 2 ? (int)(d > (size_t)maxd ? (size_t)maxd : d) : 0;
+}
 
 struct SlideArgs {
   const void* in;
@@ -42,6 +94,7 @@ struct SlideArgs {
   int chunks;       // channel chunks (gridDim.x = chunks * groups)
   int seg_rows;     // output rows per segment
   int per_sample;   // 1: blockIdx.y is the sample (per-sample weights / pooling / DyMN epilogue); 0: CTAs stride over samples
+  int depth;        // prefetch ring depth in rows (RING kernels)
   const float* xscale;
   const float* xshift;
   const float* scale;
@@ -58,7 +111,7 @@ struct SlideArgs {
 // MODE 0: training forward (optional input BN+act XACT >= 0, raw output + batch statistics)
 // MODE 1: eval forward (folded BN + act epilogue, SE pooling, DyMN DyReLU-B / coordinate attention)
 // MODE 2: stride-1 data gradient (mirrored taps, optional residual-gradient add)
-template <typename T, int K, int S, int P, int MODE, int XACT, int MINB>
+template <typename T, int K, int S, int P, int MODE, int XACT, int MINB, bool RING>
 __global__ void __launch_bounds__(kST, MINB) dw_slide_kernel(const SlideArgs a) {
   constexpr int V = Vec<T>::N;
   constexpr int NIN = (P - 1) * S + K, PAD = (K - 1) / 2, KK = K * K;
@@ -77,6 +130,9 @@ __global__ void __launch_bounds__(kST, MINB) dw_slide_kernel(const SlideArgs a) 
   float* s_sq = s_sum + a.cvc * V;             // [cc]
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
+  // prefetch ring: [depth][NIN][kST] 16-byte vectors behind the tables
+  const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(s_sq + a.cvc * V) + (uint32_t)tid * 16u;
+  const unsigned char* ringp = reinterpret_cast<const unsigned char*>(s_sq + a.cvc * V) + tid * 16;
   {
     const float* wsrc = a.wt + (size_t)b * a.dy.wt_bstride + (size_t)cv0 * V;
     for (int i = tid; i < KK * cc; i += kST) {
@@ -192,16 +248,39 @@ __global__ void __launch_bounds__(kST, MINB) dw_slide_kernel(const SlideArgs a) 
 #pragma unroll
           for (int i = 0; i < V; ++i) acc[l][p][i] = 0.f;
 
+      // ring: feed q of this unit reads input row i0 + q (S = 2: even rows are the Ph0 feeds, odd rows the Ph1 feeds)
+      const int steps = nrows + L - 1;
+      const int nfeed = S == 1 ? steps : 2 * steps - 1;
+      int rs = 0;                                             // ring slot of the next feed
+      auto issue = [&](int q, int slot_) {
+        if (RING) {
+          const int irow = i0 + q;
+          if (q < nfeed && irow >= 0 && irow < F) {
+            const T* rp = colp + (long long)irow * rowstride;
+            const uint32_t dst = ring0 + (uint32_t)(slot_ * NIN) * (kST * 16u);
+#pragma unroll
+            for (int j = 0; j < NIN; ++j)
+              if ((cmask >> j) & 1u) cp_async<16>(dst + (uint32_t)j * (kST * 16u), rp + (size_t)j * C);
+          }
+          cp_commit();
+        }
+      };
+      if (RING) {
+        for (int q = 0; q < a.depth; ++q) issue(q, q);
+      }
+      int fq = 0;                                             // feeds consumed so far
       // one input row: load, transform once, scatter into the live output rows.  PH = row parity for S = 2.
-      auto feed = [&](int irow, auto ph_tag) {
+      auto feed_row = [&](int irow, auto ph_tag) {
         constexpr int PH = decltype(ph_tag)::value;
         if (irow < 0 || irow >= F) return;
         const T* rp = colp + (long long)irow * rowstride;
         float v[NIN][V];
 #pragma unroll
         for (int j = 0; j < NIN; ++j) {
-          if ((cmask >> j) & 1u) Vec<T>::load(rp + (size_t)j * C, v[j]);
-          else {
+          if ((cmask >> j) & 1u) {
+            if (RING) Vec<T>::load(reinterpret_cast<const T*>(ringp + (size_t)(rs * NIN + j) * (kST * 16)), v[j]);
+            else Vec<T>::load(rp + (size_t)j * C, v[j]);
+          } else {
 #pragma unroll
             for (int i = 0; i < V; ++i) v[j][i] = 0.f;
           }
@@ -237,11 +316,19 @@ __global__ void __launch_bounds__(kST, MINB) dw_slide_kernel(const SlideArgs a) 
             for (int p = 0; p < P; ++p) {
               const int kx = ix - p * S;
               if (kx >= 0 && kx < K) {
-#pragma unroll
-                for (int i = 0; i < V; ++i) acc[sl][p][i] = fmaf(v[ix][i], w[kx][i], acc[sl][p][i]);
+                fma_vec<V>(v[ix], w[kx], acc[sl][p]);
               }
             }
           }
+        }
+      };
+      auto feed = [&](int irow, auto ph_tag) {
+        if (RING) cp_wait_pending(a.depth - 1);               // this feed's row has landed (own copies only)
+        feed_row(irow, ph_tag);
+        if (RING) {                                           // the slot just consumed takes the row `depth` feeds ahead
+          issue(fq + a.depth, rs);
+          ++fq;
+          if (++rs == a.depth) rs = 0;
         }
       };
       using Ph0 = std::integral_constant<int, 0>;
@@ -251,7 +338,6 @@ __global__ void __launch_bounds__(kST, MINB) dw_slide_kernel(const SlideArgs a) 
       //   S = 1: input row i0 + n, kernel row ky feeds slot K-1-ky; slot 0 is complete afterwards.
       //   S = 2: input row i0 + 2n (even kernel rows) completes slot 0; after the shift row i0 + 2n + 1 feeds
       //          the odd kernel rows.
-      const int steps = nrows + L - 1;
       for (int n = 0; n < steps; ++n) {
         feed(i0 + n * S, Ph0{});
         const int orel = n - (L - 1);
@@ -330,11 +416,20 @@ inline SlidePlan plan_slide(int B, int Fo, int To, int cv, int V, int P, int S, 
 }
 
 template <typename T, int K, int S, int P, int MODE, int XACT, int MINB>
-void launch_one(const SlideArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
-  auto kern = dw_slide_kernel<T, K, S, P, MODE, XACT, MINB>;
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr = true; }
-  kern<<<grid, kST, smem, st>>>(a);
+void launch_one(SlideArgs a, dim3 grid, size_t smem, cudaStream_t st) {
+  constexpr int NIN = (P - 1) * S + K;
+  const size_t slot = (size_t)NIN * kST * 16;
+  a.depth = ring_depth((size_t)(227 * 1024) / MINB - 1024, smem, slot, a.cvc * Vec<T>::N <= 32 ? 3 : 2);
+  static unsigned long long mask0 = 0, mask1 = 0;
+  if (a.depth > 0) {
+    auto kern = dw_slide_kernel<T, K, S, P, MODE, XACT, MINB, true>;
+    if (eat_opt_in_smem(kern, 200 * 1024, mask1) != EAT_OK) return;
+    kern<<<grid, kST, smem + a.depth * slot, st>>>(a);
+  } else {
+    auto kern = dw_slide_kernel<T, K, S, P, MODE, XACT, MINB, false>;
+    if (eat_opt_in_smem(kern, 64 * 1024, mask0) != EAT_OK) return;
+    kern<<<grid, kST, smem, st>>>(a);
+  }
 }
 
 template <typename T, int K, int S, int P, int MINB>
@@ -411,11 +506,12 @@ struct WgArgs {
   int B, F, Tn, Fo, To, C;
   int cvc, chunks, seg_rows;
   int per_sample;   // 1: blockIdx.y is the sample (per-sample gradient tables, DyMN)
+  int depth;        // prefetch ring depth in steps (RING kernels)
   const float* xscale;
   const float* xshift;
 };
 
-template <typename T, int K, int S, int P, int V, int XACT, int MINB>
+template <typename T, int K, int S, int P, int V, int XACT, int MINB, bool RING>
 __global__ void __launch_bounds__(kST, MINB) dw_wgrad_slide_kernel(const WgArgs a) {
   constexpr int KK = K * K, PAD = (K - 1) / 2;
   constexpr int NIN = (P - 1) * S + K;
@@ -430,6 +526,10 @@ __global__ void __launch_bounds__(kST, MINB) dw_wgrad_slide_kernel(const WgArgs 
   const int cc = ncv * V;
   float* s_acc = smem;                         // [KK][cc]
   const int tid = threadIdx.x;
+  // prefetch ring behind the table: [depth][NV][kST] vectors of VB bytes; NV = P dz vectors + NIN input vectors per row
+  constexpr int VB = V * (int)sizeof(T), NV = P + NIN * S;
+  const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(s_acc + KK * a.cvc * V) + (uint32_t)tid * VB;
+  const unsigned char* ringp = reinterpret_cast<const unsigned char*>(s_acc + KK * a.cvc * V) + tid * VB;
   for (int i = tid; i < KK * cc; i += kST) s_acc[i] = 0.f;
   __syncthreads();
   const int ppb = kST / ncv;
@@ -515,8 +615,7 @@ __global__ void __launch_bounds__(kST, MINB) dw_wgrad_slide_kernel(const WgArgs 
             for (int kx = 0; kx < K; ++kx)
 #pragma unroll
               for (int p = 0; p < P; ++p)
-#pragma unroll
-                for (int i = 0; i < V; ++i) wacc[ky * K + kx][i] = fmaf(dzw[sl][p][i], v[p * S + kx][i], wacc[ky * K + kx][i]);
+                fma_vec<V, !(K == 3 && S == 2)>(dzw[sl][p], v[p * S + kx], wacc[ky * K + kx]);
           }
         };
         using Ph0 = std::integral_constant<int, 0>;
@@ -549,7 +648,76 @@ __global__ void __launch_bounds__(kST, MINB) dw_wgrad_slide_kernel(const WgArgs 
               for (int i = 0; i < V; ++i) dzw[L - 1][p][i] = 0.f;
           }
         };
-        if (S == 2) {
+        if constexpr (RING) {
+          // step n's operands (dz row n, input row i0 + n, or rows i0 + 2n and i0 + 2n + 1 for stride 2) travel as ONE
+          // cp.async group into slot n % depth; the thread reads back only its own copies
+          auto rows_of = [&](int n, int& ie, bool& ev, bool& od) {
+            ie = i0 + n * S;
+            ev = ie >= 0 && ie < F;
+            od = S == 2 && (n < nrows + (K - 3) / 2) && ie + 1 >= 0 && ie + 1 < F;
+          };
+          auto issue = [&](int n, int slot_) {
+            if (n < steps) {
+              const uint32_t dst = ring0 + (uint32_t)(slot_ * NV) * (kST * VB);
+              if (n < nrows) {
+                const T* gp = dzp + (size_t)n * To * C;
+#pragma unroll
+                for (int p = 0; p < P; ++p)
+                  if (to0 + p < To) cp_async<VB>(dst + (uint32_t)p * (kST * VB), gp + (size_t)p * C);
+              }
+              int ie; bool ev, od;
+              rows_of(n, ie, ev, od);
+              if (ev) {
+                const T* rp = colp + (long long)ie * rowstride;
+#pragma unroll
+                for (int j = 0; j < NIN; ++j)
+                  if ((cmask >> j) & 1u) cp_async<VB>(dst + (uint32_t)(P + j) * (kST * VB), rp + (size_t)j * C);
+              }
+              if (od) {
+                const T* rp = colp + (long long)(ie + 1) * rowstride;
+#pragma unroll
+                for (int j = 0; j < NIN; ++j)
+                  if ((cmask >> j) & 1u) cp_async<VB>(dst + (uint32_t)(P + NIN + j) * (kST * VB), rp + (size_t)j * C);
+              }
+            }
+            cp_commit();
+          };
+          auto fetch = [&](int slot_, int first, float (&v)[NIN][V]) {
+#pragma unroll
+            for (int j = 0; j < NIN; ++j) {
+              if ((cmask >> j) & 1u) VecW<T, V>::load(reinterpret_cast<const T*>(ringp + (size_t)(slot_ * NV + first + j) * (kST * VB)), v[j]);
+              else {
+#pragma unroll
+                for (int i = 0; i < V; ++i) v[j][i] = 0.f;
+              }
+            }
+          };
+          for (int q = 0; q < a.depth; ++q) issue(q, q);
+          int rs = 0;
+          for (int n = 0; n < steps; ++n) {
+            cp_wait_pending(a.depth - 1);
+#pragma unroll
+            for (int l = 0; l + 1 < L; ++l)
+#pragma unroll
+              for (int p = 0; p < P; ++p)
+#pragma unroll
+                for (int i = 0; i < V; ++i) dzw[l][p][i] = dzw[l + 1][p][i];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+              if (n < nrows && to0 + p < To) VecW<T, V>::load(reinterpret_cast<const T*>(ringp + (size_t)(rs * NV + p) * (kST * VB)), dzw[L - 1][p]);
+              else {
+#pragma unroll
+                for (int i = 0; i < V; ++i) dzw[L - 1][p][i] = 0.f;
+              }
+            }
+            int ie; bool ev, od;
+            rows_of(n, ie, ev, od);
+            if (ev) { fetch(rs, P, ve); mac(Ph0{}, Ph0{}); }
+            if (od) { fetch(rs, P + NIN, ve); mac(Ph0{}, Ph1{}); }
+            issue(n + a.depth, rs);
+            if (++rs == a.depth) rs = 0;
+          }
+        } else if (S == 2) {
           for (int n = 0; n < steps; ++n) {
             slide_window(n);
             const int ie = i0 + 2 * n, io = ie + 1;                   // odd kernel rows reach dz rows n .. n-(K-3)/2
@@ -589,16 +757,31 @@ __global__ void __launch_bounds__(kST, MINB) dw_wgrad_slide_kernel(const WgArgs 
   }
 }
 
+template <typename T, int K, int S, int P, int V, int XACT, int MINB>
+int launch_wg_one(WgArgs a, dim3 grid, size_t smem, cudaStream_t st) {
+  constexpr int NIN = (P - 1) * S + K;
+  const size_t slot = (size_t)(P + NIN * S) * kST * V * sizeof(T);
+  a.depth = ring_depth((size_t)(227 * 1024) / MINB - 1024, smem, slot, S == 1 ? 2 : 0);   // stride 2: a slot holds two input rows, the ring costs a CTA
+  static unsigned long long mask1 = 0;
+  if (a.depth > 0) {
+    auto kern = dw_wgrad_slide_kernel<T, K, S, P, V, XACT, MINB, true>;
+    if (int rc = eat_opt_in_smem(kern, 200 * 1024, mask1)) return rc;
+    kern<<<grid, kST, smem + a.depth * slot, st>>>(a);
+  } else {
+    dw_wgrad_slide_kernel<T, K, S, P, V, XACT, MINB, false><<<grid, kST, smem, st>>>(a);
+  }
+  return EAT_OK;
+}
+
 template <typename T, int K, int S, int P, int V, int MINB>
 int launch_wg_act(const WgArgs& a, int xact_code, dim3 grid, size_t smem, cudaStream_t st) {
   switch (xact_code) {
-    case -1: dw_wgrad_slide_kernel<T, K, S, P, V, -1, MINB><<<grid, kST, smem, st>>>(a); break;
-    case EAT_ACT_NONE: dw_wgrad_slide_kernel<T, K, S, P, V, EAT_ACT_NONE, MINB><<<grid, kST, smem, st>>>(a); break;
-    case EAT_ACT_RELU: dw_wgrad_slide_kernel<T, K, S, P, V, EAT_ACT_RELU, MINB><<<grid, kST, smem, st>>>(a); break;
-    case EAT_ACT_HSWISH: dw_wgrad_slide_kernel<T, K, S, P, V, EAT_ACT_HSWISH, MINB><<<grid, kST, smem, st>>>(a); break;
+    case -1: return launch_wg_one<T, K, S, P, V, -1, MINB>(a, grid, smem, st);
+    case EAT_ACT_NONE: return launch_wg_one<T, K, S, P, V, EAT_ACT_NONE, MINB>(a, grid, smem, st);
+    case EAT_ACT_RELU: return launch_wg_one<T, K, S, P, V, EAT_ACT_RELU, MINB>(a, grid, smem, st);
+    case EAT_ACT_HSWISH: return launch_wg_one<T, K, S, P, V, EAT_ACT_HSWISH, MINB>(a, grid, smem, st);
     default: eat_set_error("dw wgrad slide: unsupported input activation"); return EAT_ERR_UNSUPPORTED;
   }
-  return EAT_OK;
 }
 
 // K = 3: 4 fp32 (8 bf16) channels per thread; K = 5 (fp32 only): 2 channels per thread, 25 x 2 tap accumulators
@@ -633,9 +816,10 @@ struct Dg2Args {
   int B, F, Tn, Fo, To, C;
   int cvc, chunks, seg_rows;   // seg_rows counts row PAIRS
   int per_sample;
+  int depth;                   // prefetch ring depth in dz rows (RING kernels)
 };
 
-template <typename T, int K, int MINB>
+template <typename T, int K, int MINB, bool RING>
 __global__ void __launch_bounds__(kST, MINB) dw_dgrad2_slide_kernel(const Dg2Args a) {
   constexpr int V = Vec<T>::N;
   constexpr int Q = 4, PAD = (K - 1) / 2, KK = K * K;
@@ -650,6 +834,8 @@ __global__ void __launch_bounds__(kST, MINB) dw_dgrad2_slide_kernel(const Dg2Arg
   const int cc = ncv * V;
   float* s_w = smem;                             // [KK][cc]
   const int tid = threadIdx.x;
+  const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(s_w + KK * a.cvc * V) + (uint32_t)tid * 16u;   // [depth][NDZ][kST] x 16 B
+  const unsigned char* ringp = reinterpret_cast<const unsigned char*>(s_w + KK * a.cvc * V) + tid * 16;
   {
     const float* wsrc = a.wt + (a.per_sample ? (size_t)blockIdx.y * a.wt_bstride : 0) + (size_t)cv0 * V;
     for (int i = tid; i < KK * cc; i += kST) {
@@ -703,8 +889,26 @@ __global__ void __launch_bounds__(kST, MINB) dw_dgrad2_slide_kernel(const Dg2Arg
       }
     };
     // prefill: rows m_a - PAD/2 .. m_a + LW - 2 - PAD/2 go to slots 1 .. LW-1 (they shift down by one in step 0)
+    // ring: step mm needs dz row m_a + mm - PAD/2 + LW - 1; one cp.async group per step, own copies only
+    auto issue = [&](int mm, int slot_) {
+      if (RING) {
+        const int o = m_a + mm - PAD / 2 + LW - 1;
+        if (mm < npair && o >= 0 && o < Fo) {
+          const T* rp = colp + (long long)o * To * C;
+          const uint32_t dst = ring0 + (uint32_t)(slot_ * NDZ) * (kST * 16u);
+#pragma unroll
+          for (int j = 0; j < NDZ; ++j)
+            if ((cmask >> j) & 1u) cp_async<16>(dst + (uint32_t)j * (kST * 16u), rp + (size_t)j * C);
+        }
+        cp_commit();
+      }
+    };
+    if (RING) {
+      for (int q = 0; q < a.depth; ++q) issue(q, q);
+    }
 #pragma unroll
     for (int l = 1; l < LW; ++l) load_row(m_a - PAD / 2 + l - 1, win[l]);
+    int rs = 0;
     for (int mm = 0; mm < npair; ++mm) {
       const int m = m_a + mm;
 #pragma unroll
@@ -713,7 +917,22 @@ __global__ void __launch_bounds__(kST, MINB) dw_dgrad2_slide_kernel(const Dg2Arg
         for (int j = 0; j < NDZ; ++j)
 #pragma unroll
           for (int i = 0; i < V; ++i) win[l][j][i] = win[l + 1][j][i];
-      load_row(m - PAD / 2 + LW - 1, win[LW - 1]);
+      if (RING) {
+        cp_wait_pending(a.depth - 1);
+        const int o = m - PAD / 2 + LW - 1;
+#pragma unroll
+        for (int j = 0; j < NDZ; ++j) {
+          if (o >= 0 && o < Fo && ((cmask >> j) & 1u)) Vec<T>::load(reinterpret_cast<const T*>(ringp + (size_t)(rs * NDZ + j) * (kST * 16)), win[LW - 1][j]);
+          else {
+#pragma unroll
+            for (int i = 0; i < V; ++i) win[LW - 1][j][i] = 0.f;
+          }
+        }
+        issue(mm + a.depth, rs);
+        if (++rs == a.depth) rs = 0;
+      } else {
+        load_row(m - PAD / 2 + LW - 1, win[LW - 1]);
+      }
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int irow = 2 * m + r;
@@ -739,8 +958,7 @@ __global__ void __launch_bounds__(kST, MINB) dw_dgrad2_slide_kernel(const Dg2Arg
             for (int q = 0; q < Q; ++q) {
               if (((q + PAD - kx) & 1) != 0) continue;
               const int j = (q + PAD - kx) / 2 + PAD / 2;
-#pragma unroll
-              for (int i = 0; i < V; ++i) acc[q][i] = fmaf(win[sl][j][i], w[i], acc[q][i]);
+              fma_vec<V>(win[sl][j], w, acc[q]);
             }
           }
         }
@@ -774,11 +992,25 @@ int launch_dg2_slide(Dg2Args a, int k, cudaStream_t st) {
   a.chunks = pl.chunks; a.cvc = pl.cvc; a.seg_rows = pl.seg_rows;
   dim3 grid(pl.chunks * pl.groups, pl.gy);
   const size_t smem = (size_t)k * k * a.cvc * V * sizeof(float);
-  if (k == 3) dw_dgrad2_slide_kernel<T, 3, 4><<<grid, kST, smem, st>>>(a);
-  else {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(dw_dgrad2_slide_kernel<T, 5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr = true; }
-    dw_dgrad2_slide_kernel<T, 5, 3><<<grid, kST, smem, st>>>(a);
+  constexpr int NDZ3 = 4 / 2 + 1 / 2 + 1, NDZ5 = 4 / 2 + 2 / 2 + 1;
+  static unsigned long long m3 = 0, m5 = 0, m5n = 0;
+  if (k == 3) {
+    const size_t slot = (size_t)NDZ3 * kST * 16;
+    a.depth = ring_depth((size_t)(227 * 1024) / 4 - 1024, smem, slot, 0);       // 3x3: measured slower with the ring
+    if (a.depth > 0) {
+      if (int rc = eat_opt_in_smem(dw_dgrad2_slide_kernel<T, 3, 4, true>, 200 * 1024, m3)) return rc;
+      dw_dgrad2_slide_kernel<T, 3, 4, true><<<grid, kST, smem + a.depth * slot, st>>>(a);
+    } else dw_dgrad2_slide_kernel<T, 3, 4, false><<<grid, kST, smem, st>>>(a);
+  } else {
+    const size_t slot = (size_t)NDZ5 * kST * 16;
+    a.depth = ring_depth((size_t)(227 * 1024) / 3 - 1024, smem, slot, 2);
+    if (a.depth > 0) {
+      if (int rc = eat_opt_in_smem(dw_dgrad2_slide_kernel<T, 5, 3, true>, 200 * 1024, m5)) return rc;
+      dw_dgrad2_slide_kernel<T, 5, 3, true><<<grid, kST, smem + a.depth * slot, st>>>(a);
+    } else {
+      if (int rc = eat_opt_in_smem(dw_dgrad2_slide_kernel<T, 5, 3, false>, 64 * 1024, m5n)) return rc;
+      dw_dgrad2_slide_kernel<T, 5, 3, false><<<grid, kST, smem, st>>>(a);
+    }
   }
   EAT_CHECK_LAUNCH();
   return EAT_OK;
