@@ -6,6 +6,8 @@
 // statistics (training).  Reference semantics: torchvision ConvNormActivation as used at
 // models/mn/model.py:125-133 and models/mn/block_types.py:140-170; SqueezeExcitation
 // models/mn/block_types.py:72-83.
+#include <cstdlib>
+
 #include "common.cuh"
 #include <stdlib.h>
 
@@ -566,7 +568,9 @@ int launch_dw(const T* in, const float* wt, T* out, int B, int F, int Tn, int C,
   const int mode_ = (scale != nullptr || pool != nullptr || dy.theta != nullptr || dy.ca_f != nullptr) ? 1 : ((flip || res != nullptr) ? 2 : 0);
   // sliding-window kernel (dw_slide.cu) for every 3x3 case and the 5x5 training forward; the 5x5 eval / data-gradient
   // cases stay on the shared-memory tile kernel below (measured faster there: profiles/README.md)
-  if ((stride == 1 || stride == 2) && (k == 3 || (k == 5 && mode_ == 0)) && !(mode_ == 2 && stride != 1))
+  const char* e5 = getenv("EAT_DW5_DGRAD");                  // "slide": 5x5 stride-1 data gradient on the sliding-window kernel
+  const bool slide5 = e5 != nullptr && e5[0] == 's';
+  if ((stride == 1 || stride == 2) && (k == 3 || (k == 5 && (mode_ == 0 || (mode_ == 2 && slide5)))) && !(mode_ == 2 && stride != 1))
     return dw_slide_launch(in, wt, out, V == 8 ? EAT_BF16 : EAT_F32, B, F, Tn, C, k, stride, xf, scale, shift, act, res, flip,
                            pool, ssum, ssq, st, dy);
   if (k != 5) { eat_set_error("dw conv: only k in {3,5}, stride in {1,2}"); return EAT_ERR_UNSUPPORTED; }

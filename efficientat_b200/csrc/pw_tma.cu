@@ -62,7 +62,7 @@ using namespace tc;
 using namespace tma;
 
 constexpr int BM = 128;
-constexpr int BN_MAX = 128;
+constexpr int BN_MAX = 256;           // widest N tile (one UMMA instruction covers it: M = 128, N <= 256)
 constexpr int A_TILE = BM * 128;        // 16 KB
 constexpr int kThreads = 320;           // TMA warp, MMA warp, 4 fix-up warps, 4 epilogue warps
 constexpr int kMmaWarp = 1, kFirstFix = 2, kFirstEpi = 6;
@@ -71,6 +71,7 @@ constexpr int STG_BYTES = 32 * 128;     // one staged 32 x 32 fp32 sub-tile
 struct TmaParams {
   int M, N, K;
   int BN, n_tiles, m_tiles, k_blocks, r_blocks;   // r_blocks: residual k-blocks per tile (0: no residual)
+  int bnp;                                        // BN rounded up to 128 / 256: stride of the per-column shared-memory tables
   int stages, wres;                               // wres != 0: weight hi/lo tiles resident per N tile
   int n_acc, acc_cols, tmem_cols;                 // TMEM accumulators in flight (n_acc * acc_cols <= tmem_cols columns)
   int stg_bufs;                                   // staging buffers per epilogue warp (1 or 2)
@@ -110,8 +111,8 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
   unsigned char* s_stg = smem + p.off_stg;               // [4 epilogue warps][stg_bufs][4 KB]
   float* s_isc = reinterpret_cast<float*>(smem + p.off_f);             // [kpad] in-transform scale (0 beyond K)
   float* s_ish = s_isc + p.kpad;                                       // [kpad]
-  float* s_shift = s_ish + p.kpad;                                     // [BN_MAX] epilogue shift of the current N tile
-  float* s_stat = s_shift + BN_MAX;                                    // [4][2][BN_MAX]
+  float* s_shift = s_ish + p.kpad;                                     // [bnp] epilogue shift of the current N tile
+  float* s_stat = s_shift + p.bnp;                                     // [4][2][bnp]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   const int S = p.stages;
   const uint32_t bar_full = smem_u32(bars), bar_ready = bar_full + 8 * S, bar_empty = bar_ready + 8 * S;
@@ -151,7 +152,7 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       s_ish[i] = i < p.K ? p.in_shift[i] : 0.f;
     }
   }
-  for (int i = threadIdx.x; i < 8 * BN_MAX; i += kThreads) s_stat[i] = 0.f;
+  for (int i = threadIdx.x; i < 8 * p.bnp; i += kThreads) s_stat[i] = 0.f;
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -279,12 +280,16 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const bool fold = EPI != 0 && p.scale != nullptr;
     auto do_fix_w = [&](unsigned char* w, int kb, int n0) {
       const int lg = pair_lg(p.K - kb * KB);
-      if (fold) {
-        if (lg == 2) fix_w<2, true>(w, ft, BN, p.scale, n0, p.N);
-        else fix_w<1, true>(w, ft, BN, p.scale, n0, p.N);
-      } else {
-        if (lg == 2) fix_w<2, false>(w, ft, BN, nullptr, n0, p.N);
-        else fix_w<1, false>(w, ft, BN, nullptr, n0, p.N);
+      for (int h = 0; h < BN; h += 128) {                      // one pass covers 128 weight rows
+        unsigned char* wh = w + (size_t)h * 128;
+        const int rows = min(128, BN - h);
+        if (fold) {
+          if (lg == 2) fix_w<2, true>(wh, ft, rows, p.scale, n0 + h, p.N);
+          else fix_w<1, true>(wh, ft, rows, p.scale, n0 + h, p.N);
+        } else {
+          if (lg == 2) fix_w<2, false>(wh, ft, rows, nullptr, n0 + h, p.N);
+          else fix_w<1, false>(wh, ft, rows, nullptr, n0 + h, p.N);
+        }
       }
     };
     TT_DECL
@@ -334,22 +339,27 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const int ew = warp - kFirstEpi;
     const int etid = threadIdx.x - kFirstEpi * 32;            // 0..127
     unsigned char* stg = s_stg + (size_t)ew * p.stg_bufs * STG_BYTES;
-    float* my_stat = s_stat + ew * 2 * BN_MAX;
+    constexpr int NC = BN_MAX / 32;                           // 32-column chunks of the widest tile
+    const int bnp = p.bnp;
+    float* my_stat = s_stat + ew * 2 * bnp;
     const bool do_stats = EPI == 0 && p.stat_sum != nullptr;
-    float csum[4] = {0.f, 0.f, 0.f, 0.f}, csq[4] = {0.f, 0.f, 0.f, 0.f};
+    float csum[NC], csq[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { csum[c] = 0.f; csq[c] = 0.f; }
     int cur_nt = -1, acc = 0, cb = 0;
     uint32_t acc_phase = 0;
     TT_DECL
     auto flush_stats = [&](int nt_old) {
       // lane partials -> shared, combine the four warps, one fp64 atomic per channel
 #pragma unroll
-      for (int c = 0; c < 4; ++c) { my_stat[c * 32 + lane] = csum[c]; my_stat[BN_MAX + c * 32 + lane] = csq[c]; csum[c] = 0.f; csq[c] = 0.f; }
+      for (int c = 0; c < NC; ++c)
+        if (c * 32 < bnp) { my_stat[c * 32 + lane] = csum[c]; my_stat[bnp + c * 32 + lane] = csq[c]; csum[c] = 0.f; csq[c] = 0.f; }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (etid < BN) {
-        const int n = nt_old * BN + etid;
+      for (int e = etid; e < BN; e += 128) {
+        const int n = nt_old * BN + e;
         float a = 0.f, b = 0.f;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) { a += s_stat[w * 2 * BN_MAX + etid]; b += s_stat[w * 2 * BN_MAX + BN_MAX + etid]; }
+        for (int w = 0; w < 4; ++w) { a += s_stat[w * 2 * bnp + e]; b += s_stat[w * 2 * bnp + bnp + e]; }
         if (n < p.N) { atomicAdd(p.stat_sum + n, (double)a); atomicAdd(p.stat_sq + n, (double)b); }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -362,7 +372,7 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         if (do_stats && cur_nt >= 0) flush_stats(cur_nt);
         if (EPI != 0) {
           asm volatile("bar.sync 2, 128;" ::: "memory");       // everyone is done with the previous tile's shifts
-          if (etid < BN) s_shift[etid] = (p.shift != nullptr && n0 + etid < p.N) ? p.shift[n0 + etid] : 0.f;
+          for (int e = etid; e < BN; e += 128) s_shift[e] = (p.shift != nullptr && n0 + e < p.N) ? p.shift[n0 + e] : 0.f;
           asm volatile("bar.sync 2, 128;" ::: "memory");
         }
         cur_nt = nt;
@@ -376,7 +386,7 @@ pw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       const int row0 = m0 + q * 32;
       const int rows_left = min(32, p.tile_rps - row0);       // <= 0: nothing of this warp's slab is inside the sample
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < NC; ++c) {
         if (c * 32 < BN && n0 + c * 32 < p.N) {
           unsigned char* buf = stg + (size_t)cb * STG_BYTES;
           // the store issued from this buffer (two chunks ago, or the previous one with a single buffer) has drained
@@ -528,13 +538,25 @@ struct WeightWs { int trans; void* ws; size_t bytes; const float* att; int dyn_k
 
 template <int EPI, int XACT>
 int launch_tma(const void* A, const float* W, void* C, const void* R, TmaParams p, cudaStream_t st, WeightWs ws) {
-  // ---- tiling
-  if (p.N <= BN_MAX) { p.BN = ceil_div(p.N, 16) * 16; p.n_tiles = 1; }
+  // ---- tiling.  Shared-memory traffic per k-block of one M tile is n_tiles * (TMA write 16 KB + fix-up 32 KB + 24 KB of A
+  // operand reads) + 320 B per padded output column: wide N tiles amortise the A side, which is what bounds the K >= 80
+  // layers.  Tiles above 128 columns hold ONE accumulator per CTA (256 TMEM columns when two CTAs share the SM), so they are
+  // used only when the main loop is long enough to dwarf the epilogue (k_blocks >= kWideMinKb).
+  int bn_max = 208, wide_min_kb = 5;      // 208: widest tile whose streamed weight stage still lets two CTAs share the SM
+  if (const char* e = getenv("EAT_TMA_BNMAX")) { const int v = atoi(e); if (v >= 64 && v <= BN_MAX) bn_max = v; }
+  if (const char* e = getenv("EAT_TMA_WIDE_MINKB")) wide_min_kb = atoi(e);
+  if (ceil_div(p.K, KB) < wide_min_kb && bn_max > 128) bn_max = 128;
+  if (p.N <= bn_max) { p.BN = ceil_div(p.N, 16) * 16; p.n_tiles = 1; }
   else {                                   // several N tiles: multiples of 32 so that no store chunk straddles two tiles
-    int best = 128, best_pad = ceil_div(p.N, 128) * 128;
-    for (int bn : {96, 64}) { const int pad = ceil_div(p.N, bn) * bn; if (pad < best_pad) { best = bn; best_pad = pad; } }
+    int best = 0; long long best_cost = 0;
+    for (int bn = 64; bn <= bn_max; bn += 32) {
+      const long long nt = ceil_div(p.N, bn);
+      const long long cost = nt * 72 * 1024 + nt * bn * 320;
+      if (best == 0 || cost < best_cost || (cost == best_cost && bn > best)) { best = bn; best_cost = cost; }
+    }
     p.BN = best; p.n_tiles = ceil_div(p.N, best);
   }
+  p.bnp = p.BN <= 128 ? 128 : 256;
   if (p.n_samples < 1) { p.n_samples = 1; p.tile_rps = p.M; }
   p.tps = ceil_div(p.tile_rps, BM);
   p.m_tiles = p.n_samples * p.tps;
@@ -548,7 +570,7 @@ int launch_tma(const void* A, const float* W, void* C, const void* R, TmaParams 
   const size_t w_tile = (size_t)p.BN * 128;
   const size_t w_res = (size_t)p.k_blocks * w_tile;
   const size_t ident = p.r_blocks > 0 ? 4096 : 0;
-  const size_t floats = (2 * (size_t)p.kpad + BN_MAX + 8 * BN_MAX) * 4;
+  const size_t floats = (2 * (size_t)p.kpad + 9 * (size_t)p.bnp) * 4;
   const size_t barsz = (3 * 8 + 17) * 8 + 16;
   auto fixed = [&](int bufs) { return ident + (size_t)bufs * 4 * STG_BYTES + floats + barsz + 1024 /*alignment slack*/; };
   int ctas = 1;
@@ -560,7 +582,8 @@ int launch_tma(const void* A, const float* W, void* C, const void* R, TmaParams 
     for (int bufs = 2; bufs >= 1 && ctas == 1; --bufs)
       if (fixed(bufs) + w_res + 3 * (size_t)A_TILE <= half) { ctas = 2; p.stg_bufs = bufs; }
     // large K: stream the weight k-blocks with A (stage = A tile + W tile); two CTAs still fit with >= 2 stages each
-    if (ctas == 1 && fixed(2) + 2 * ((size_t)A_TILE + w_tile) <= half) { ctas = 2; p.stg_bufs = 2; stream2 = true; }
+    for (int bufs = 2; bufs >= 1 && ctas == 1; --bufs)
+      if (fixed(bufs) + 2 * ((size_t)A_TILE + w_tile) <= half) { ctas = 2; p.stg_bufs = bufs; stream2 = true; }
   }
   const size_t limit = ctas == 2 ? half : kSmemLimit;
   p.wres = ctas == 2 ? (stream2 ? 0 : 1) : ((fixed(2) + w_res + 4 * (size_t)A_TILE <= kSmemLimit) ? 1 : 0);
@@ -571,7 +594,7 @@ int launch_tma(const void* A, const float* W, void* C, const void* R, TmaParams 
   if (p.stages < 2) { eat_set_error("pw_tma: shared-memory budget exceeded (K too large for the in-transform tables)"); return EAT_ERR_UNSUPPORTED; }
   // TMEM: n_acc accumulators of acc_cols (>= BN) columns; 256 columns per CTA when two CTAs share the SM
   p.tmem_cols = ctas == 2 ? 256 : 512;
-  p.acc_cols = p.BN <= 32 ? 32 : (p.BN <= 64 ? 64 : 128);
+  p.acc_cols = p.BN <= 32 ? 32 : (p.BN <= 64 ? 64 : (p.BN <= 128 ? 128 : 256));
   p.n_acc = p.tmem_cols / p.acc_cols;
   if (p.n_acc > 8) p.n_acc = 8;
   if (const char* e = getenv("EAT_TMA_NACC")) { const int v = atoi(e); if (v >= 1 && v <= p.n_acc) p.n_acc = v; }

@@ -13,6 +13,8 @@ SHAPES = [  # (M, N, K)
     (4096, 64, 16), (4000, 24, 64), (1300, 72, 24), (777, 40, 72), (2048, 120, 40), (1024, 240, 40),
     (640, 80, 240), (512, 200, 80), (384, 480, 80), (300, 112, 480), (256, 672, 112), (128, 160, 672),
     (1024, 960, 160), (130, 960, 160), (20000, 16, 16), (256, 3840, 640), (129, 8, 8),
+    # N tiles wider than 128 columns (K >= 160): one ragged tile of 208, 3 x 160, one of 192, 4 x 192 with a clipped last tile
+    (1000, 200, 160), (515, 480, 192), (900, 184, 200), (260, 672, 192), (700, 160, 960),
 ]
 
 
