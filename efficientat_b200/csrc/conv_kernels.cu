@@ -566,10 +566,12 @@ int launch_dw(const T* in, const float* wt, T* out, int B, int F, int Tn, int C,
   const int pad = (k - 1) / 2;
   const int Fo = (F + 2 * pad - k) / stride + 1, To = (Tn + 2 * pad - k) / stride + 1;
   const int mode_ = (scale != nullptr || pool != nullptr || dy.theta != nullptr || dy.ca_f != nullptr) ? 1 : ((flip || res != nullptr) ? 2 : 0);
-  // sliding-window kernel (dw_slide.cu) for every 3x3 case and the 5x5 training forward; the 5x5 eval / data-gradient
-  // cases stay on the shared-memory tile kernel below (measured faster there: profiles/README.md)
-  const char* e5 = getenv("EAT_DW5_DGRAD");                  // "slide": 5x5 stride-1 data gradient on the sliding-window kernel
-  const bool slide5 = e5 != nullptr && e5[0] == 's';
+  // sliding-window kernel (dw_slide.cu) for every 3x3 case and the 5x5 training forward; the 5x5 eval and wide
+  // data-gradient cases stay on the shared-memory tile kernel below (measured faster there: profiles/README.md)
+  // 5x5 stride-1 data gradient: sliding-window kernel up to 256 channels (199 vs 211 us at C = 120), tile kernel above
+  // (125 vs 131 us at C = 960); EAT_DW5_DGRAD=slide|tile forces one
+  const char* e5 = getenv("EAT_DW5_DGRAD");
+  const bool slide5 = e5 != nullptr ? e5[0] == 's' : C <= 256;
   if ((stride == 1 || stride == 2) && (k == 3 || (k == 5 && (mode_ == 0 || (mode_ == 2 && slide5)))) && !(mode_ == 2 && stride != 1))
     return dw_slide_launch(in, wt, out, V == 8 ? EAT_BF16 : EAT_F32, B, F, Tn, C, k, stride, xf, scale, shift, act, res, flip,
                            pool, ssum, ssq, st, dy);

@@ -27,8 +27,9 @@ namespace {
 using namespace tc;
 using namespace tma;
 
-constexpr int MB = 64;                  // reduction rows per pipeline stage
-constexpr int BOX = MB * 128;           // 8 KB: one landed [64 x 32 fp32] box
+// MB = reduction rows per pipeline stage (template parameter): 64, or 128 for launches with few boxes per stage, where the
+// per-block costs (barrier round trips, TMA issue, fix-up prologue) rather than bytes set the pace.
+// BOX = MB * 128 bytes: one landed [MB x 32 fp32] box.
 constexpr int GB = 2;                   // G boxes per stage: 64 output channels -> 128 accumulator rows
 constexpr int kThreads = 320;
 constexpr int kMmaWarp = 1, kFirstFix = 2, kFirstEpi = 6;
@@ -36,7 +37,8 @@ constexpr int kMmaWarp = 1, kFirstFix = 2, kFirstEpi = 6;
 struct WgParams {
   float* dW;
   int M, N, K;
-  int n_tiles, k_tiles, xb;             // xb: X boxes per stage (uniform over the tiles of a launch, <= 4 = 128 channels)
+  int n_tiles, k_tiles, xb;             // xb: X boxes reserved per stage (<= 4 = 128 channels); a CTA loads only those inside K
+  int gbs;                              // G boxes reserved per stage (1 when N <= 32, else 2); a CTA loads only those inside N
   int rows_per_split, sample_rows, splits_per_sample;
   int stages;
   uint32_t stage_bytes, off_f, off_bar;
@@ -56,9 +58,10 @@ __device__ __forceinline__ uint32_t idesc_mn(int n) {       // D fp32, A/B bf16,
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-template <int XACT>
+template <int XACT, int MB>
 __global__ void __launch_bounds__(kThreads, 2)
 wgrad_tma_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapX, const WgParams p) {
+  constexpr int BOX = MB * 128;
   extern __shared__ __align__(1024) unsigned char smem[];
   float* s_isc = reinterpret_cast<float*>(smem + p.off_f);          // [128] in-transform scale of this CTA's channels
   float* s_ish = s_isc + 128;
@@ -87,7 +90,12 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant
     if (m_end > p.M) m_end = p.M;
   }
   const int n_blocks = m_end > m_begin ? (int)((m_end - m_begin + MB - 1) / MB) : 0;
-  const int xb = p.xb;
+  // boxes of this CTA's tile that hold real channels.  A box that is not loaded leaves its accumulator rows / columns
+  // undefined (the MMA shape stays 128 x 64*xb so that the operand atoms keep their LBO spacing); the epilogue never
+  // reads them (n < N, kb < K tests below).
+  const int gb = min(p.gbs, (p.N - n0 + KB - 1) / KB);
+  const int xb = min(p.xb, (p.K - k0 + KB - 1) / KB);
+  const uint32_t x_off = (uint32_t)p.gbs * BOX;
   const uint32_t stage_base = smem_u32(smem);
 
   if (threadIdx.x == 0) {
@@ -121,10 +129,9 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant
         const int m = (int)(m_begin + (long long)blk * MB);
         mbar_wait(bar_empty + 8 * s, ph ^ 1u);
         const uint32_t dst = stage_base + (uint32_t)s * p.stage_bytes;
-        mbar_expect_tx(bar_full + 8 * s, (uint32_t)(GB + xb) * BOX);
-#pragma unroll
-        for (int b = 0; b < GB; ++b) tma_load_2d(&mapG, bar_full + 8 * s, dst + b * BOX, n0 + b * KB, m);
-        for (int b = 0; b < xb; ++b) tma_load_2d(&mapX, bar_full + 8 * s, dst + (GB + b) * BOX, k0 + b * KB, m);
+        mbar_expect_tx(bar_full + 8 * s, (uint32_t)(gb + xb) * BOX);
+        for (int b = 0; b < gb; ++b) tma_load_2d(&mapG, bar_full + 8 * s, dst + b * BOX, n0 + b * KB, m);
+        for (int b = 0; b < xb; ++b) tma_load_2d(&mapX, bar_full + 8 * s, dst + x_off + b * BOX, k0 + b * KB, m);
         if (++s == S) { s = 0; ph ^= 1u; }
       }
     }
@@ -132,13 +139,13 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant
   } else if (warp == kMmaWarp) {
     // ================================================================= MMA issuer (one thread)
     if (lane == 0) {
-      const uint32_t idesc = idesc_mn(64 * xb);
+      const uint32_t idesc = idesc_mn(64 * p.xb);
       int s = 0;
       uint32_t ph = 0;
       for (int blk = 0; blk < n_blocks; ++blk) {
         mbar_wait(bar_ready + 8 * s, ph);
         tc_fence_after();
-        const uint32_t sg = stage_base + (uint32_t)s * p.stage_bytes, sx = sg + GB * BOX;
+        const uint32_t sg = stage_base + (uint32_t)s * p.stage_bytes, sx = sg + x_off;
         const long long mb = m_begin + (long long)blk * MB;
         const int rows = (int)min((long long)MB, m_end - mb);
         const int steps = (rows + 15) >> 4;
@@ -166,12 +173,11 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant
       if (p.gate != nullptr) { b0 = (int)(mb / p.rps); off0 = (int)(mb - (long long)b0 * p.rps); }
       mbar_wait(bar_full + 8 * s, ph);
       unsigned char* st = smem + (size_t)s * p.stage_bytes;
-#pragma unroll
-      for (int b = 0; b < GB; ++b)                               // gradient boxes: plain split (rows past the split zeroed)
+      for (int b = 0; b < gb; ++b)                               // gradient boxes: plain split (rows past the split zeroed)
         fix_a<2, -1, MB>(st + b * BOX, ft, rows_valid, nullptr, nullptr, 0, nullptr, 0, 0, 1, 0);
       for (int b = 0; b < xb; ++b) {
         const int kl = b * KB + (ft & 3) * 8;                      // channel of this thread's chunk pair, local to the CTA
-        fix_a<2, XACT, MB>(st + (GB + b) * BOX, ft, rows_valid, s_isc - k0, s_ish - k0, k0 + kl, p.gate, off0, b0, p.rps, p.K);
+        fix_a<2, XACT, MB>(st + x_off + b * BOX, ft, rows_valid, s_isc - k0, s_ish - k0, k0 + kl, p.gate, off0, b0, p.rps, p.K);
       }
       fence_proxy_async();
       __syncwarp();
@@ -218,8 +224,9 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant
   }
 }
 
-template <int XACT>
-int launch_wg(const float* G, const float* X, WgParams p, cudaStream_t st) {
+template <int XACT, int MB>
+int launch_wg_mb(const float* G, const float* X, WgParams p, cudaStream_t st) {
+  constexpr int BOX = MB * 128;
   p.n_tiles = ceil_div(p.N, 64);
   p.k_tiles = ceil_div(p.K, 128);
   const int kt = p.K < 128 ? p.K : 128;
@@ -248,7 +255,8 @@ int launch_wg(const float* G, const float* X, WgParams p, cudaStream_t st) {
     p.rows_per_split = (int)rows;
     p.splits_per_sample = 0;
   }
-  p.stage_bytes = (uint32_t)((GB + p.xb) * BOX);
+  p.gbs = p.N <= KB ? 1 : GB;
+  p.stage_bytes = (uint32_t)((p.gbs + p.xb) * BOX);
   const size_t budget = (227 * 1024 - 2048) / 2;
   const size_t misc = 2 * 128 * 4 + (3 * 8 + 1) * 8 + 16 + 1024;
   p.stages = (int)((budget - misc) / p.stage_bytes);
@@ -262,10 +270,20 @@ int launch_wg(const float* G, const float* X, WgParams p, cudaStream_t st) {
   if (int rc = make_map(&mG, G, p.M, p.N, MB)) return rc;
   if (int rc = make_map(&mX, X, p.M, p.K, MB)) return rc;
   static unsigned long long attr_mask = 0;
-  if (int rc = eat_opt_in_smem(wgrad_tma_kernel<XACT>, budget, attr_mask)) return rc;
-  wgrad_tma_kernel<XACT><<<tiles * splits, kThreads, smem, st>>>(mG, mX, p);
+  if (int rc = eat_opt_in_smem(wgrad_tma_kernel<XACT, MB>, budget, attr_mask)) return rc;
+  wgrad_tma_kernel<XACT, MB><<<tiles * splits, kThreads, smem, st>>>(mG, mX, p);
   EAT_CHECK_LAUNCH();
   return EAT_OK;
+}
+
+template <int XACT>
+int launch_wg(const float* G, const float* X, const WgParams& p, cudaStream_t st) {
+  // 128-row blocks when a stage holds at most three boxes (N <= 64 and K <= 32, or N <= 32 and K <= 64) and the
+  // reduction is long: the first layers of the network, M in the millions
+  const int boxes = (p.N <= KB ? 1 : GB) + ceil_div(p.K < 128 ? p.K : 128, KB);
+  int mb = (boxes <= 3 && p.sample_rows == 0 && p.M >= (1 << 20)) ? 128 : 64;
+  if (const char* e = getenv("EAT_WG_MB")) { const int v = atoi(e); if (v == 64 || (v == 128 && boxes <= 3)) mb = v; }
+  return mb == 128 ? launch_wg_mb<XACT, 128>(G, X, p, st) : launch_wg_mb<XACT, 64>(G, X, p, st);
 }
 
 int launch_wg_x(const float* G, const float* X, const WgParams& p, cudaStream_t st) {
@@ -282,7 +300,7 @@ extern "C" int eat_pw_tma_wgrad(const float* G, const float* X, float* dW, long 
                                 int per_sample, cudaStream_t st) {
   if (M == 0) return EAT_OK;
   if (K % 4 != 0 || N % 4 != 0) { eat_set_error("pw_tma_wgrad: K and N must be multiples of 4"); return EAT_ERR_ARG; }
-  if (M >= (1ll << 31) - MB) { eat_set_error("pw_tma_wgrad: M too large"); return EAT_ERR_ARG; }
+  if (M >= (1ll << 31) - 128) { eat_set_error("pw_tma_wgrad: M too large"); return EAT_ERR_ARG; }
   if ((in_scale == nullptr) != (in_shift == nullptr)) { eat_set_error("pw_tma_wgrad: in_scale and in_shift come together"); return EAT_ERR_ARG; }
   if (in_act == EAT_ACT_SIGMOID) { eat_set_error("pw_tma_wgrad: sigmoid input activation is not offered"); return EAT_ERR_UNSUPPORTED; }
   if ((((uintptr_t)G) | ((uintptr_t)X) | ((uintptr_t)dW) | ((uintptr_t)gate)) & 15) { eat_set_error("pw_tma_wgrad: operands must be 16-byte aligned"); return EAT_ERR_ARG; }
