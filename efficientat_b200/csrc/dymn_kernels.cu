@@ -187,6 +187,8 @@ __global__ void __launch_bounds__(256) dy_act_bwd_kernel(const T* __restrict__ d
   float a1[4], a2[4], b1[4], b2[4], sc[4], sh[4], ct[4];
   float g_ct[4] = {0.f, 0.f, 0.f, 0.f}, g_a1[4] = {0.f, 0.f, 0.f, 0.f}, g_a2[4] = {0.f, 0.f, 0.f, 0.f};
   float g_b1[4] = {0.f, 0.f, 0.f, 0.f}, g_b2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { a1[k] = a2[k] = b1[k] = b2[k] = sc[k] = sh[k] = ct[k] = 0.f; }
   if (live) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -197,7 +199,13 @@ __global__ void __launch_bounds__(256) dy_act_bwd_kernel(const T* __restrict__ d
     }
     const float4 t4 = *reinterpret_cast<const float4*>(c.ca_t + ((size_t)b * To + to) * C + c0);
     ct[0] = t4.x; ct[1] = t4.y; ct[2] = t4.z; ct[3] = t4.w;
-    for (int fo = 0; fo < Fo; ++fo) {
+  }
+  // every thread walks the rows (the d(ca_f) partial sums of the four output columns a warp holds for one channel vector
+  // are combined with shuffles before they reach shared memory: one atomic per channel and warp instead of four
+  // conflicting ones -- shared fp32 atomics are compare-and-swap loops)
+  for (int fo = 0; fo < Fo; ++fo) {
+    float dcf[4] = {0.f, 0.f, 0.f, 0.f};
+    if (live) {
       const size_t off = (((size_t)b * Fo + fo) * To + to) * C + c0;
       float g[4], zv[4], o[4];
       V4<T>::load(dp + off, g);
@@ -211,20 +219,38 @@ __global__ void __launch_bounds__(256) dy_act_bwd_kernel(const T* __restrict__ d
         const bool sel = l1 >= l2;
         const float r = sel ? l1 : l2;
         const float dr = g[k] * cf[k] * ct[k];
-        atomicAdd(&s_caf[fo * 32 + cvec * 4 + k], g[k] * r * ct[k]);
+        dcf[k] = g[k] * r * ct[k];
         g_ct[k] = fmaf(g[k] * r, cf[k], g_ct[k]);
         o[k] = dr * (sel ? a1[k] : a2[k]);
         if (sel) { g_a1[k] = fmaf(dr, u, g_a1[k]); g_b1[k] += dr; } else { g_a2[k] = fmaf(dr, u, g_a2[k]); g_b2[k] += dr; }
       }
       V4<T>::store(du + off, o);
     }
-    float* dct = dcat + ((size_t)b * To + to) * C + c0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      dct[k] = g_ct[k];
-      atomicAdd(&s_coef[(cvec * 4 + k) * 4 + 0], g_a1[k]); atomicAdd(&s_coef[(cvec * 4 + k) * 4 + 1], g_a2[k]);
-      atomicAdd(&s_coef[(cvec * 4 + k) * 4 + 2], g_b1[k]); atomicAdd(&s_coef[(cvec * 4 + k) * 4 + 3], g_b2[k]);
+      dcf[k] += __shfl_xor_sync(0xffffffffu, dcf[k], 8);
+      dcf[k] += __shfl_xor_sync(0xffffffffu, dcf[k], 16);
     }
+    if ((threadIdx.x & 31) < 8) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) atomicAdd(&s_caf[fo * 32 + cvec * 4 + k], dcf[k]);
+    }
+  }
+  // DyReLU coefficient gradients: same shuffle combine, then one atomic per coefficient and warp
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float v[4] = {g_a1[k], g_a2[k], g_b1[k], g_b2[k]};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] += __shfl_xor_sync(0xffffffffu, v[j], 8);
+      v[j] += __shfl_xor_sync(0xffffffffu, v[j], 16);
+      if ((threadIdx.x & 31) < 8) atomicAdd(&s_coef[(cvec * 4 + k) * 4 + j], v[j]);
+    }
+  }
+  if (live) {
+    float* dct = dcat + ((size_t)b * To + to) * C + c0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dct[k] = g_ct[k];
   }
   __syncthreads();
   for (int i = threadIdx.x; i < Fo * 32; i += 256) {
