@@ -659,8 +659,8 @@ int launch_dw_bwd(int which, const void* dz, const float* wt, const void* in, In
     size_t smem = ((size_t)IR * IT * 32 + (size_t)FR * TT * 32 + (size_t)k * k * 32) * sizeof(float);
 #define EAT_WG(KK, SS)                                                                                          \
   do {                                                                                                          \
-    static bool attr = false;                                                                                   \
-    if (!attr) { cudaFuncSetAttribute(dw_wgrad_tile_kernel<T, KK, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); attr = true; } \
+    static unsigned long long attr = 0;                                                                         \
+    if (int rc = eat_opt_in_smem(dw_wgrad_tile_kernel<T, KK, SS>, 128 * 1024, attr)) return rc;                 \
     dw_wgrad_tile_kernel<T, KK, SS><<<grid, kThreads, smem, st>>>((const T*)dz, (const T*)in, xf, dw, F, Tn, Fo, To, C, dw_bstride); \
   } while (0)
     if (k == 3 && stride == 1) EAT_WG(3, 1); else if (k == 3 && stride == 2) EAT_WG(3, 2);

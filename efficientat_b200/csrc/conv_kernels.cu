@@ -588,8 +588,8 @@ int launch_dw(const T* in, const float* wt, T* out, int B, int F, int Tn, int C,
   const int tmode = (scale != nullptr || pool != nullptr || dy.theta != nullptr || dy.ca_f != nullptr) ? 1 : ((flip || res != nullptr) ? 2 : 0);
 #define EAT_DWM(KK, SS, MM)                                                                                     \
   do {                                                                                                          \
-    static bool attr = false;                                                                                   \
-    if (!attr) { cudaFuncSetAttribute(dw_tile_kernel<T, KK, SS, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; } \
+    static unsigned long long attr = 0;                                                                         \
+    if (int rc = eat_opt_in_smem(dw_tile_kernel<T, KK, SS, MM>, 100 * 1024, attr)) return rc;                   \
     dw_tile_kernel<T, KK, SS, MM><<<grid, kThreads, smem, st>>>(in, wt, out, F, Tn, Fo, To, C, xf, scale, shift, act, res, flip, pool, ssum, ssq, dy); \
   } while (0)
 #define EAT_DW(KK, SS) do { if (tmode == 0) EAT_DWM(KK, SS, 0); else if (tmode == 1) EAT_DWM(KK, SS, 1); else EAT_DWM(KK, SS, 2); } while (0)
