@@ -44,6 +44,8 @@ def parse():
                     help="train: the headline training step; eval: mel + forward only (BASELINE.json configs[1])")
     ap.add_argument("--cpu-baseline-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sync-readback", action="store_true",
+                    help="e2e loop: read the loss back with a blocking .cpu() after every step instead of the pipelined LossReader")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -531,21 +533,37 @@ def run_ours(args):
     # ---- end to end: pinned host buffers -> H2D -> step -> D2H loss, every step.  The copies go through the package's
     # double-buffered HostPrefetcher (batch i+1 is copied on a side stream while step i runs, as a pinned-memory
     # DataLoader would); all K copies and K loss read-backs happen inside the timed region.
-    from efficientat_b200.train import HostPrefetcher
+    # The loss read-back is pipelined through the package's LossReader: step i's result is copied into pinned host memory
+    # behind step i and collected while step i+1 is already queued (--sync-readback restores `loss.cpu()` after every
+    # step, which leaves the device idle while the host enqueues the next step: ~0.9 ms per step).
+    from efficientat_b200.train import HostPrefetcher, LossReader
     pf = HostPrefetcher(dev)
+    rd = LossReader(dev)
     barrier()
     t0 = time.perf_counter()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     pf.submit(0, (wave_h, y_h, t_h, k_h))
+    losses_read = 0
     for i in range(args.steps):
         if i + 1 < args.steps:
             pf.submit((i + 1) % 2, (wave_h, y_h, t_h, k_h))
         w_d, y_d, t_d, k_d = pf.get(i % 2)
         loss = trainer.step(w_d, y_d, t_d, k_d)
         pf.release(i % 2)
-        loss_host = loss.cpu()                      # device -> host read of the step's result (synchronises)
+        if args.sync_readback:
+            loss_host = loss.cpu()                  # device -> host read of the step's result (synchronises)
+            losses_read += 1
+        else:
+            rd.push(loss)                           # asynchronous device -> host copy of step i's result ...
+            if i:
+                loss_host = rd.pop()                # ... and the host collects step i-1's while step i runs
+                losses_read += 1
+    if not args.sync_readback:
+        loss_host = rd.pop()
+        losses_read += 1
     e3.record()
+    assert losses_read == args.steps
     barrier()
     ms_e2e = e2.elapsed_time(e3)
     if world > 1:
@@ -582,7 +600,9 @@ def run_ours(args):
                        "precision_mode": args.precision, "cuda_graph": (not args.no_graph) and args.mode == "train",
                        "l2": "inputs (waveforms %.0f MB/GPU) exceed L2; no explicit flush" % (wave.numel() * 4 / 1e6)},
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "readback": "loss.cpu() after every step" if args.sync_readback else
+                    "every step's loss, asynchronous copy into pinned memory collected one step behind (LossReader)"},
             "gpu_launches": launches_per_step * args.steps, "host_enqueue_ms_per_step": host_ms,
             "clocks": clocks.summary(),
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -1,7 +1,20 @@
-"""Host-side helpers the reference scripts import from helpers/utils.py (NAME_TO_WIDTH :1-32, LR schedule
-:56-84, mixup :90-95).  Pure Python / numpy, re-implemented with the same semantics."""
+"""Host-side helpers the reference scripts import from helpers/utils.py (NAME_TO_WIDTH :1-32, label table :35-46, LR
+schedule :56-84, mixup :90-95).  Pure Python / numpy, re-implemented with the same semantics."""
+import csv
+import os
+
 import numpy as np
 import torch
+
+
+def load_labels(path="metadata/class_labels_indices.csv"):
+    """-> (display names, ids) of the AudioSet classes from the reference's metadata file (helpers/utils.py:38-46 reads
+    it relative to the CWD at import time); two empty lists when the file is not there."""
+    if not os.path.exists(path):
+        return [], []
+    with open(path, "r") as f:
+        lines = list(csv.reader(f, delimiter=","))
+    return [l[2] for l in lines[1:]], [l[1] for l in lines[1:]]
 
 _MN_WIDTH = {"mn01": 0.1, "mn02": 0.2, "mn04": 0.4, "mn05": 0.5, "mn06": 0.6, "mn08": 0.8, "mn10": 1.0, "mn12": 1.2,
              "mn14": 1.4, "mn16": 1.6, "mn20": 2.0, "mn30": 3.0, "mn40": 4.0}

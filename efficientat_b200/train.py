@@ -60,6 +60,53 @@ class HostPrefetcher:
         self.free[slot].record(torch.cuda.current_stream(self.device))
 
 
+class LossReader:
+    """Pipelined device -> host read-back of per-step results (the loss), for loops that log every step.
+
+    The reference's loop calls `.item()` three times per step (ex_audioset.py:192-194): the host then waits for the
+    device after EVERY step, and the device idles while the host enqueues the next one.  Here `push(t)` enqueues an
+    asynchronous copy of the small device tensor into a pinned host slot behind the step that produced it, and `pop()`
+    returns the OLDEST outstanding value, waiting only for that step's event.  Popping one step behind keeps the host a
+    step ahead of the device; every step's value still reaches the host, in order.
+
+        rd = LossReader(device)
+        for i, batch in enumerate(batches):
+            rd.push(trainer.step(*batch))
+            if i: log(rd.pop())          # loss of step i-1, step i is already queued
+        log(rd.pop())
+    """
+
+    def __init__(self, device, depth=2):
+        self.device = torch.device(device)
+        self.depth = int(depth)
+        self.slots = [None] * self.depth
+        self.events = [torch.cuda.Event() for _ in range(self.depth)]
+        self.head = 0                    # next slot to write
+        self.pending = 0
+
+    def push(self, t):
+        if self.pending == self.depth:
+            raise RuntimeError("LossReader: all slots are outstanding; pop() before the next push()")
+        if not t.is_cuda:
+            raise RuntimeError("LossReader.push expects a CUDA tensor")
+        k = self.head
+        if self.slots[k] is None or self.slots[k].shape != t.shape or self.slots[k].dtype != t.dtype:
+            self.slots[k] = torch.empty(t.shape, dtype=t.dtype, device="cpu").pin_memory()
+        with torch.cuda.device(self.device):
+            self.slots[k].copy_(t.detach(), non_blocking=True)       # stream-ordered behind the producing step
+            self.events[k].record(torch.cuda.current_stream(self.device))
+        self.head = (k + 1) % self.depth
+        self.pending += 1
+
+    def pop(self):
+        if self.pending == 0:
+            raise RuntimeError("LossReader.pop without an outstanding push")
+        k = (self.head - self.pending) % self.depth
+        self.events[k].synchronize()
+        self.pending -= 1
+        return self.slots[k].clone()
+
+
 class AudioSetTrainer:
     """The body of the reference's training loop (ex_audioset.py:120-201) on device-resident tensors.
 

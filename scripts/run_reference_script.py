@@ -121,11 +121,15 @@ def main():
     ap.add_argument("--no-dropout", action="store_true")
     ap.add_argument("--log-json", default=None)
     ap.add_argument("--keep-checkpoint", default=None, help="copy the last checkpoint the script saved to this path")
+    ap.add_argument("--export-ensemble-in-mn-model", action="store_true",
+                    help="--side reference only: windowed_inference.py:8 imports get_ensemble_model from models.mn.model, "
+                         "which the reference defines in models/ensemble.py only; bind the reference's own function under "
+                         "that name on the imported module (no file is edited) so the script can run for golden numbers")
     ap.add_argument("script")
     ap.add_argument("rest", nargs=argparse.REMAINDER)
     a = ap.parse_args()
     ref_root = os.path.abspath(a.ref_root)
-    script = os.path.join(ref_root, a.script)
+    script = os.path.join(ref_root, a.script)          # an absolute path (a driver under tests/golden/) is taken as is
     if not os.path.isfile(script):
         raise SystemExit(f"{script} not found (run `python baseline/make_ref.py` where the reference checkout exists)")
     rest = a.rest[1:] if a.rest and a.rest[0] == "--" else a.rest
@@ -155,6 +159,12 @@ def main():
         torch.manual_seed(a.seed)
         np.random.seed(a.seed)
         random.seed(a.seed)
+
+    if a.export_ensemble_in_mn_model and a.side == "reference":
+        import models.ensemble
+        import models.mn.model
+        if not hasattr(models.mn.model, "get_ensemble_model"):
+            models.mn.model.get_ensemble_model = models.ensemble.get_ensemble_model
 
     sys.argv = [script] + rest
     runpy.run_path(script, run_name="__main__")

@@ -182,6 +182,49 @@ def golden_script():
     print("script: epochs", [e["train_loss"] for e in res["epochs"]], "top1", res["inference_top10"][0])
 
 
+def golden_script_f4():
+    """SURVEY section 8 row f4 (ensemble + windowed inference), reference modules on CPU, fp32:
+      * `inference.py --ensemble mn04_as mn10_as` on the wav fixture, unchanged (models/ensemble.py: mean of the logits);
+        (an ensemble with a DyMN member is pinned at the synthetic golden inputs instead, tests/test_gpu_f4.py: on this
+        recording the synthetic DyMN states overflow -- logits of 1e20 with the reference's own modules -- and pin nothing);
+      * `windowed_inference.py` (2 s windows, 1 s hop -> 9 windows of the 10 s fixture): the script's own printout and,
+        through tests/golden/windowed_driver.py, EATagger's full-precision result for mn10_as and for the mn04 + mn10 ensemble.
+    windowed_inference.py:8 cannot be imported against the reference's own package (it asks models.mn.model for
+    get_ensemble_model, which lives in models/ensemble.py); the launcher binds that name on the imported module."""
+    import json
+    import re
+    import tempfile
+    from tests import refscripts as R
+    os.chdir(REPO)
+    wav = os.path.join(R.ref_root(), "resources", "metro_station-paris.wav")
+    res = {"window_s": 2.0, "hop_s": 1.0, "ensemble": ["mn04_as", "mn10_as"]}
+    with tempfile.TemporaryDirectory() as wd:
+        env = R.make_workdir(wd, checkpoints=("mn04_as", "mn10_as"))
+        r = R.run_script(wd, "reference", "inference.py", ["--ensemble"] + res["ensemble"] + ["--audio_path", wav], env,
+                         no_dropout=False)
+        assert r.returncode == 0, r.stderr[-3000:]
+        rows = re.findall(r"^(.+): (\d\.\d{3})$", r.stdout, flags=re.M)
+        assert len(rows) == 10, r.stdout
+        res["inference_ensemble_top10"] = [[a, float(b)] for a, b in rows]
+        r = R.run_script(wd, "reference", "windowed_inference.py",
+                         ["--model", "mn10_as", "--audio_path", wav, "--window_size", "2", "--hop_length", "1"], env,
+                         no_dropout=False, extra=["--export-ensemble-in-mn-model"])
+        assert r.returncode == 0, r.stderr[-3000:]
+        res["windowed_stdout"] = R.parse_windowed_stdout(r.stdout)
+        assert len(res["windowed_stdout"]) == 9, r.stdout
+        for key, names in (("windowed_mn10", ["mn10_as"]), ("windowed_ensemble", res["ensemble"])):
+            out = os.path.join(wd, key + ".json")
+            r = R.run_script(wd, "reference", os.path.join(HERE, "windowed_driver.py"),
+                             [out, wav, "2", "1", "cpu"] + names, env, no_dropout=False,
+                             extra=["--export-ensemble-in-mn-model"])
+            assert r.returncode == 0, r.stderr[-3000:]
+            res[key] = json.load(open(out))
+            assert len(res[key]) == 9
+    with open(os.path.join(HERE, "script_f4.json"), "w") as fh:
+        json.dump(res, fh, indent=0)
+    print("script_f4: ensemble top1", res["inference_ensemble_top10"][0], "windowed[0]", res["windowed_mn10"][0]["tags"][0], "windowed ensemble[0]", res["windowed_ensemble"][0]["tags"][0])
+
+
 JOBS = {
     "mel": golden_mel,
     "mn10": lambda: run_net("mn10", ref_mn, 1.0, 64000, 2),
@@ -195,6 +238,7 @@ JOBS = {
     "dymn20": lambda: run_net("dymn20", ref_dymn, 2.0, 64000, 2),
     "mn40_10s": lambda: run_net("mn40_10s", ref_mn, 4.0, 320000, 1, train=False),
     "script": golden_script,
+    "script_f4": golden_script_f4,
 }
 
 if __name__ == "__main__":

@@ -11,7 +11,7 @@ import torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LAUNCHER = os.path.join(REPO, "scripts", "run_reference_script.py")
 RELEASE_FILE = {"mn04_as": "mn04_as_mAP_432.pt", "mn10_as": "mn10_as_mAP_471.pt", "dymn04_as": "dymn04_as.pt",
-                "dymn10_as": "dymn10_as.pt"}
+                "dymn10_as": "dymn10_as.pt"}            # models/mn/model.py:18-70, models/dymn/model.py:18-33
 
 # the script-level golden configuration (tests/golden/make_golden.py::golden_script and tests/test_gpu_refscripts.py)
 SCRIPT_ENV = {"EAT_SYNTH_CLIP_SECONDS": "1", "EAT_SYNTH_TRAIN_CLIPS": "40", "EAT_SYNTH_TEST_CLIPS": "527"}
@@ -61,9 +61,10 @@ def make_workdir(path, checkpoints=("mn04_as",), env=None):
     return e
 
 
-def run_script(workdir, side, script, args, env, seed=0, no_dropout=True, log_json=None, keep_checkpoint=None, timeout=1200):
+def run_script(workdir, side, script, args, env, seed=0, no_dropout=True, log_json=None, keep_checkpoint=None, timeout=1200,
+               extra=()):
     root = ref_root()
-    cmd = [sys.executable, LAUNCHER, "--side", side, "--ref-root", root, "--seed", str(seed)]
+    cmd = [sys.executable, LAUNCHER, "--side", side, "--ref-root", root, "--seed", str(seed)] + list(extra)
     if no_dropout:
         cmd.append("--no-dropout")
     if log_json:
@@ -78,3 +79,19 @@ def run_script(workdir, side, script, args, env, seed=0, no_dropout=True, log_js
 def read_log(path):
     with open(path) as f:
         return json.load(f)
+
+
+def parse_windowed_stdout(text):
+    """windowed_inference.py:144-148 prints `Window: s - e` followed by five `\t<tag>: <p:.2f>` lines per window
+    -> [{"start": s, "end": e, "tags": [[tag, p], ...]}]"""
+    import re
+    out = []
+    for line in text.splitlines():
+        m = re.match(r"^Window: (\d+\.\d+) - (\d+\.\d+)$", line.strip())
+        if m:
+            out.append({"start": float(m.group(1)), "end": float(m.group(2)), "tags": []})
+            continue
+        m = re.match(r"^\t(.+): (\d\.\d{2})$", line)
+        if m and out:
+            out[-1]["tags"].append([m.group(1), float(m.group(2))])
+    return out

@@ -138,3 +138,26 @@ def test_host_prefetcher_feeds_the_trainer_in_order():
     for i, vals in enumerate(seen):
         got = [v.item() for v in vals]
         assert got == [float(i), float(i), float(-i), float(-i)], (i, got)
+
+
+def test_loss_reader_returns_every_step_in_order():
+    """LossReader: values pushed from a reused device tensor (the graph trainer returns the same tensor every step)
+    come back in order, one step behind, and over-/under-flow raise."""
+    from efficientat_b200.train import LossReader
+    dev = torch.device("cuda", 0)
+    rd = LossReader(dev)
+    out = torch.zeros(2, device=dev, dtype=torch.float64)
+    got = []
+    for i in range(6):
+        torch.cuda._sleep(1_000_000)
+        out.fill_(float(i))                        # "step i" overwrites the static output
+        rd.push(out)
+        if i:
+            got.append(rd.pop())
+    got.append(rd.pop())
+    assert [g.tolist() for g in got] == [[float(i)] * 2 for i in range(6)]
+    with pytest.raises(RuntimeError):
+        rd.pop()
+    rd.push(out), rd.push(out)
+    with pytest.raises(RuntimeError):
+        rd.push(out)
