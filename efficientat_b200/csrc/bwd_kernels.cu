@@ -264,6 +264,149 @@ __global__ void __launch_bounds__(kThreads) se_bwd_reduce_kernel(const T* __rest
   for (int c = threadIdx.x; c < C; c += kThreads) atomicAdd(dgate + (size_t)b * C + c, smem[c]);
 }
 
+// SE block: the squeeze-excitation reduce AND the BatchNorm-backward reduce of the depthwise output in ONE pass over
+// (dp, z).  The BatchNorm reduce needs  sum (dp * gate[b,c] + dpool[b,c]) * act'(v) * {1, z - mean}  but dpool is only known
+// after the SE MLP backward, which itself needs  dgate = sum_p dp * act(v)  -- so far three passes (dgate, reduce, apply).
+// gate and dpool are constant over the pixels of a sample, hence per (b, c)
+//   sum_p (dp * gate + dpool) * act' * w  =  gate * sum_p dp * act' * w  +  dpool * sum_p act' * w        (w = 1, z - mean)
+// and the four pixel sums can be taken in the same walk that produces dgate; a tiny kernel combines them over the batch
+// once dpool exists (se_bn_bwd_combine_kernel).  One read of the two expanded tensors less per SE block.
+//   dgate[b,c]          += sum_p dp * act(v)                       (atomics, as se_bwd_reduce_kernel)
+//   part[x][0][b][c]     = sum_p dp * act'(v)          part[x][1][b][c] = sum_p dp * act'(v) * (z - mean)
+//   part[x][2][b][c]     = sum_p act'(v)               part[x][3][b][c] = sum_p act'(v) * (z - mean)
+// x = blockIdx.x (the CTAs of a sample split its pixels; every CTA stores its slice, zeros included: no zero fill needed).
+template <typename T, int ACT>
+__global__ void __launch_bounds__(kThreads, 2) se_bn_bwd_reduce_kernel(
+    const T* __restrict__ dp, const T* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
+    const float* __restrict__ mean, float* __restrict__ dgate, float* __restrict__ part, int B, int P, int C) {
+  constexpr int V = Vec<T>::N;
+  constexpr int U = V == 4 ? 4 : 2;  // pixels per trip
+  extern __shared__ float smem[];    // [5][C], only when several pixel slots of the CTA share a channel vector
+  const int cv = C / V;
+  const int tcv = cv < kThreads ? cv : kThreads;
+  const int ppb = kThreads / tcv;
+  const int slot = threadIdx.x / tcv;
+  const int b = blockIdx.y;
+  const bool shared = ppb > 1;
+  if (shared) {
+    for (int i = threadIdx.x; i < 5 * C; i += kThreads) smem[i] = 0.f;
+    __syncthreads();
+  }
+  const size_t qs = (size_t)B * C;                                   // stride between the four quantities
+  float* const my_part = part + ((size_t)blockIdx.x * 4 * B + b) * C;
+  if (slot < ppb) {
+    for (int cvi = threadIdx.x % tcv; cvi < cv; cvi += tcv) {
+      const int c0 = cvi * V;
+      float sc[V], sh[V], mu[V], aD[V], a1[V], a2[V], e1[V], e2[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        sc[k] = scale[c0 + k]; sh[k] = shift[c0 + k]; mu[k] = mean[c0 + k];
+        aD[k] = 0.f; a1[k] = 0.f; a2[k] = 0.f; e1[k] = 0.f; e2[k] = 0.f;
+      }
+      auto one = [&](const float (&zv)[V], const float (&gv)[V]) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          const float v = fmaf(zv[k], sc[k], sh[k]);
+          const float d = ACT != EAT_ACT_NONE ? act_bwd(v, ACT) : 1.f;
+          const float f = ACT != EAT_ACT_NONE ? act_fwd(v, ACT) : v;
+          const float zc = zv[k] - mu[k];
+          const float gd = gv[k] * d;
+          aD[k] = fmaf(gv[k], f, aD[k]);
+          a1[k] += gd;
+          a2[k] = fmaf(gd, zc, a2[k]);
+          e1[k] += d;
+          e2[k] = fmaf(d, zc, e2[k]);
+        }
+      };
+      const size_t base = (size_t)b * P * C + c0;
+      const int step = gridDim.x * ppb;
+      int p = blockIdx.x * ppb + slot;
+      for (; p + (U - 1) * step < P; p += U * step) {
+        float zz[U][V], gg[U][V];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const size_t o = base + (size_t)(p + u * step) * C;
+          Vec<T>::load(z + o, zz[u]);
+          Vec<T>::load(dp + o, gg[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) one(zz[u], gg[u]);
+      }
+      for (; p < P; p += step) {
+        const size_t o = base + (size_t)p * C;
+        float z0[V], g0[V];
+        Vec<T>::load(z + o, z0);
+        Vec<T>::load(dp + o, g0);
+        one(z0, g0);
+      }
+      if (shared) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          atomicAdd(&smem[c0 + k], aD[k]);
+          atomicAdd(&smem[C + c0 + k], a1[k]);
+          atomicAdd(&smem[2 * C + c0 + k], a2[k]);
+          atomicAdd(&smem[3 * C + c0 + k], e1[k]);
+          atomicAdd(&smem[4 * C + c0 + k], e2[k]);
+        }
+      } else {                                       // this thread is the only owner of the channel vector in the CTA
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          atomicAdd(dgate + (size_t)b * C + c0 + k, aD[k]);
+          my_part[c0 + k] = a1[k];
+          my_part[qs + c0 + k] = a2[k];
+          my_part[2 * qs + c0 + k] = e1[k];
+          my_part[3 * qs + c0 + k] = e2[k];
+        }
+      }
+    }
+  }
+  if (shared) {
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+      atomicAdd(dgate + (size_t)b * C + c, smem[c]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) my_part[q * qs + c] = smem[(q + 1) * C + c];
+    }
+  }
+}
+
+// s1[c] += sum_b gate*A1 + dpool*E1,  s2[c] += invstd[c] * sum_b gate*A2 + dpool*E2, with A1, A2, E1, E2 the pixel sums of
+// se_bn_bwd_reduce_kernel (added up over its `parts` slices): what bn_bwd_reduce2_kernel<GM = 1> would have produced.
+// Block = 32 channels x 8 batch lanes; grid.y splits the batch further (fp64 atomics into the zeroed accumulators).
+__global__ void __launch_bounds__(256) se_bn_bwd_combine_kernel(const float* __restrict__ part, int parts,
+                                                                const float* __restrict__ gate,
+                                                                const float* __restrict__ dpool,
+                                                                const float* __restrict__ invstd, int B, int C,
+                                                                double* __restrict__ s1, double* __restrict__ s2) {
+  __shared__ double r1[8][33], r2[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const size_t qs = (size_t)B * C;
+  double t1 = 0.0, t2 = 0.0;
+  if (c < C) {
+    for (int b = blockIdx.y * 8 + threadIdx.y; b < B; b += gridDim.y * 8) {
+      float A1 = 0.f, A2 = 0.f, E1 = 0.f, E2 = 0.f;
+      for (int g = 0; g < parts; ++g) {
+        const float* p = part + ((size_t)g * 4 * B + b) * C + c;
+        A1 += p[0]; A2 += p[qs]; E1 += p[2 * qs]; E2 += p[3 * qs];
+      }
+      const double gt = gate != nullptr ? (double)gate[(size_t)b * C + c] : 1.0;
+      const double dv = dpool != nullptr ? (double)dpool[(size_t)b * C + c] : 0.0;
+      t1 += gt * A1 + dv * E1;
+      t2 += gt * A2 + dv * E2;
+    }
+  }
+  r1[threadIdx.y][threadIdx.x] = t1;
+  r2[threadIdx.y][threadIdx.x] = t2;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    double u1 = 0.0, u2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { u1 += r1[j][threadIdx.x]; u2 += r2[j][threadIdx.x]; }
+    atomicAdd(s1 + c, u1);
+    atomicAdd(s2 + c, u2 * (double)invstd[c]);
+  }
+}
+
 // Squeeze-excitation MLP backward for one sample per CTA (block_types.py:72-83):
 //   du2 = dgate * gate * (1 - gate); dh = W2^T du2; du1 = dh * (hidden > 0); dmean = W1^T du1
 //   dpool_out[b,c] = dmean * inv_count.   du2 / du1 are stored for the weight-gradient GEMMs.
@@ -726,6 +869,38 @@ int eat_se_bwd_reduce(const void* dp, const void* z, const float* scale, const f
     se_bwd_reduce_kernel<__nv_bfloat16><<<grid, kThreads, C * sizeof(float), st>>>((const __nv_bfloat16*)dp, (const __nv_bfloat16*)z, scale, shift, act, dgate, P, C);
   else
     se_bwd_reduce_kernel<float><<<grid, kThreads, C * sizeof(float), st>>>((const float*)dp, (const float*)z, scale, shift, act, dgate, P, C);
+  EAT_CHECK_LAUNCH();
+  return EAT_OK;
+}
+
+int eat_se_bn_bwd_reduce(const void* dp, const void* z, const float* scale, const float* shift, const float* mean, int act,
+                         float* dgate, float* part, int parts, int dtype, int B, int P, int C, cudaStream_t st) {
+  if (B == 0) return EAT_OK;
+  const int V = dtype == EAT_BF16 ? 8 : 4;
+  if (C % V != 0) { eat_set_error("se_bn_bwd_reduce: channels must be a multiple of the vector width"); return EAT_ERR_ARG; }
+  if (parts < 1 || P < 1) { eat_set_error("se_bn_bwd_reduce: parts and P must be positive"); return EAT_ERR_ARG; }
+  const int cv = C / V, tcv = cv < kThreads ? cv : kThreads, ppb = kThreads / tcv;
+  dim3 grid(parts, B);
+  const size_t sm = ppb > 1 ? 5 * (size_t)C * sizeof(float) : 0;      // ppb > 1 implies cv <= 128, i.e. at most 20 KB
+#define EAT_SEBN(TT, ACT) se_bn_bwd_reduce_kernel<TT, ACT><<<grid, kThreads, sm, st>>>((const TT*)dp, (const TT*)z, scale, shift, mean, dgate, part, B, P, C)
+#define EAT_SEBN_T(TT) do { if (act == EAT_ACT_RELU) EAT_SEBN(TT, EAT_ACT_RELU); else if (act == EAT_ACT_HSWISH) EAT_SEBN(TT, EAT_ACT_HSWISH); \
+                            else if (act == EAT_ACT_NONE) EAT_SEBN(TT, EAT_ACT_NONE); \
+                            else { eat_set_error("se_bn_bwd_reduce: activation must be none / relu / hardswish"); return EAT_ERR_UNSUPPORTED; } } while (0)
+  if (dtype == EAT_BF16) EAT_SEBN_T(__nv_bfloat16); else EAT_SEBN_T(float);
+#undef EAT_SEBN_T
+#undef EAT_SEBN
+  EAT_CHECK_LAUNCH();
+  return EAT_OK;
+}
+
+int eat_se_bn_bwd_combine(const float* part, int parts, const float* gate, const float* dpool, const float* invstd, int B,
+                          int C, double* s1, double* s2, cudaStream_t st) {
+  if (B == 0 || C == 0) return EAT_OK;
+  if (parts < 1) { eat_set_error("se_bn_bwd_combine: parts must be positive"); return EAT_ERR_ARG; }
+  int gy = ceil_div(B, 8);
+  if (gy > 16) gy = 16;
+  dim3 grid(ceil_div(C, 32), gy), block(32, 8);
+  se_bn_bwd_combine_kernel<<<grid, block, 0, st>>>(part, parts, gate, dpool, invstd, B, C, s1, s2);
   EAT_CHECK_LAUNCH();
   return EAT_OK;
 }

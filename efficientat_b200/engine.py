@@ -41,6 +41,9 @@ class _Layer:
     pass
 
 
+SE_FUSED_DEFAULT = "0"
+
+
 class _ZeroPool:
     """fp64 accumulators for BatchNorm statistics, carved from chunks that are zeroed with ONE fill each
     (a training step needs ~100 small zeroed buffers; one launch per buffer showed up as 250 tiny kernels)."""
@@ -97,6 +100,9 @@ class MNEngine:
         # weight gradients on a side stream (see _Fork): measured +1.1 % at B=256 (36.6 vs 37.0 ms/step,
         # profiles/README.md) -- both branches are HBM-bound -- so it stays an opt-in experiment
         self.fork_wgrad = os.environ.get("EAT_FORK_WGRAD", "0") == "1"
+        # SE blocks: squeeze-excitation reduce + BatchNorm-backward reduce of the depthwise output in one pass over the two
+        # expanded tensors (eat_se_bn_bwd_reduce / _combine) instead of two (eat_se_bwd_reduce, eat_bn_bwd_reduce)
+        self.se_fused = os.environ.get("EAT_SE_FUSED", SE_FUSED_DEFAULT) == "1"
         self._fork = None
         self._se_scale = {}
         self._zero_pool = _ZeroPool()
@@ -462,14 +468,18 @@ class MNEngine:
         else:
             lib().gemm_simt_wgrad(*args)
 
-    def _bn_bwd(self, gA, gate, dpool, z, sc, sv, act, B, P, C, dgamma, dbeta, dev, code=None):
-        """two-pass BatchNorm(+activation) backward -> dz (same dtype/shape as z)."""
+    def _bn_bwd(self, gA, gate, dpool, z, sc, sv, act, B, P, C, dgamma, dbeta, dev, code=None, sums=None):
+        """two-pass BatchNorm(+activation) backward -> dz (same dtype/shape as z).  `sums`: the (s1, s2) accumulators when
+        the reduce pass already happened elsewhere (SE blocks: eat_se_bn_bwd_reduce + eat_se_bn_bwd_combine)."""
         L = lib()
         st = _stream()
         code = self.dcode if code is None else code
-        s = self._zero_pool.take(2, C, dev)
-        L.bn_bwd_reduce(_ptr(gA), _ptr(gate), _ptr(dpool), z.data_ptr(), sc[0].data_ptr(), sc[1].data_ptr(),
-                        sv[0].data_ptr(), sv[1].data_ptr(), act, code, B, P, C, s[0].data_ptr(), s[1].data_ptr(), st)
+        if sums is None:
+            s = self._zero_pool.take(2, C, dev)
+            L.bn_bwd_reduce(_ptr(gA), _ptr(gate), _ptr(dpool), z.data_ptr(), sc[0].data_ptr(), sc[1].data_ptr(),
+                            sv[0].data_ptr(), sv[1].data_ptr(), act, code, B, P, C, s[0].data_ptr(), s[1].data_ptr(), st)
+        else:
+            s = sums
         coef = torch.empty(2, C, device=dev, dtype=torch.float32)
         L.bn_bwd_finalize(s[0].data_ptr(), s[1].data_ptr(), float(B * P), _ptr(dgamma), _ptr(dbeta),
                           coef[0].data_ptr(), coef[1].data_ptr(), C, st)
@@ -503,8 +513,16 @@ class MNEngine:
         if blk.se is not None:
             Sq = blk.se.fc1.out_features
             dgate = torch.zeros(B, blk.cexp, device=dev, dtype=torch.float32)
-            L.se_bwd_reduce(dp.data_ptr(), R["z2"].data_ptr(), R["sc2"][0].data_ptr(), R["sc2"][1].data_ptr(),
-                            blk.act, dgate.data_ptr(), dc, B, Po, blk.cexp, st)
+            if self.se_fused:
+                # ~12 CTAs per SM over the batch, at least ~16 pixels per slice
+                parts = max(1, min(32, (148 * 12) // B, (Po + 15) // 16))
+                part = torch.empty(parts, 4, B, blk.cexp, device=dev, dtype=torch.float32)
+                L.se_bn_bwd_reduce(dp.data_ptr(), R["z2"].data_ptr(), R["sc2"][0].data_ptr(), R["sc2"][1].data_ptr(),
+                                   R["sv2"][0].data_ptr(), blk.act, dgate.data_ptr(), part.data_ptr(), parts, dc, B, Po,
+                                   blk.cexp, st)
+            else:
+                L.se_bwd_reduce(dp.data_ptr(), R["z2"].data_ptr(), R["sc2"][0].data_ptr(), R["sc2"][1].data_ptr(),
+                                blk.act, dgate.data_ptr(), dc, B, Po, blk.cexp, st)
             du2 = torch.empty(B, blk.cexp, device=dev, dtype=torch.float32)
             du1 = torch.empty(B, Sq, device=dev, dtype=torch.float32)
             dpool = torch.empty(B, blk.cexp, device=dev, dtype=torch.float32)
@@ -515,8 +533,13 @@ class MNEngine:
                               self._wgrad(du1, R["mean"], G[blk.se.fc1.weight], G[blk.se.fc1.bias], B, Sq, blk.cexp, g_code=0, a_code=0)),
                      du2, du1)
         # depthwise: BN2 + activation (+ SE gate / squeeze gradient composed on the fly)
+        sums2 = None
+        if blk.se is not None and self.se_fused:
+            sums2 = self._zero_pool.take(2, blk.cexp, dev)
+            L.se_bn_bwd_combine(part.data_ptr(), parts, gate.data_ptr(), dpool.data_ptr(), R["sv2"][1].data_ptr(), B,
+                                blk.cexp, sums2[0].data_ptr(), sums2[1].data_ptr(), st)
         dz2 = self._bn_bwd(dp, gate, dpool, R["z2"], R["sc2"], R["sv2"], blk.act, B, Po, blk.cexp,
-                           G[blk.dw[1].weight], G[blk.dw[1].bias], dev)
+                           G[blk.dw[1].weight], G[blk.dw[1].bias], dev, sums=sums2)
         has_exp = blk.expand is not None
         dw_in = R["z1"] if has_exp else R["inp"]
         sc1 = R["sc1"] if has_exp else None

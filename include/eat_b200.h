@@ -244,6 +244,16 @@ int eat_bn_bwd_apply(const void* gA, const float* gate, const float* dpool, cons
 /* SE backward: dgate[b,c] += sum_p dp[b,p,c] * act(z[b,p,c]*scale[c]+shift[c]). */
 int eat_se_bwd_reduce(const void* dp, const void* z, const float* scale, const float* shift, int act, float* dgate,
                       int dtype, int B, int P, int C, cudaStream_t stream);
+/* SE block (block_types.py:72-83,177-181; autograd of `scale * input` and of the BatchNorm in front of it): the
+ * squeeze-excitation reduce and the BatchNorm-backward reduce of the depthwise output in ONE pass over (dp, z).
+ * dgate as eat_se_bwd_reduce; part [parts][4][B][C] fp32 (no zero fill needed) receives, per slice of the pixels,
+ * sum dp*act'(v), sum dp*act'(v)*(z-mean), sum act'(v), sum act'(v)*(z-mean) with v = z*scale+shift.  Grid = parts x B. */
+int eat_se_bn_bwd_reduce(const void* dp, const void* z, const float* scale, const float* shift, const float* mean, int act,
+                         float* dgate, float* part, int parts, int dtype, int B, int P, int C, cudaStream_t stream);
+/* ... and, once the SE MLP backward has produced dpool: s1[c] += sum_b gate*part0 + dpool*part2,
+ * s2[c] += invstd[c] * sum_b gate*part1 + dpool*part3 -- the sums eat_bn_bwd_reduce(gA = dp, gate, dpool) yields. */
+int eat_se_bn_bwd_combine(const float* part, int parts, const float* gate, const float* dpool, const float* invstd, int B,
+                          int C, double* s1, double* s2, cudaStream_t stream);
 /* SE MLP backward (per sample): du2 = dgate*gate*(1-gate), du1 = (W2^T du2)*(hidden>0),
  * dpool = (W1^T du1) * inv_count.  Weight gradients follow from du2/du1 via eat_gemm_simt_wgrad. */
 int eat_se_fc_bwd(const float* dgate, const float* gate, const float* hidden, const float* w1, const float* w2,

@@ -1,0 +1,92 @@
+"""Kernel-level checks of the BatchNorm-backward reduce passes against fp64 torch: the plain two-tensor reduce
+(eat_bn_bwd_reduce with gate / dpool composition) and the SE-block variant that takes the squeeze-excitation sum and the four
+BatchNorm pixel sums in ONE pass (eat_se_bn_bwd_reduce) and combines them over the batch once dpool is known
+(eat_se_bn_bwd_combine).  Autograd of block_types.py:72-83 (`scale * input`) in front of a training-mode BatchNorm +
+activation (block_types.py:150-162)."""
+import pytest
+import torch
+
+from efficientat_b200._lib import lib
+
+pytestmark = pytest.mark.gpu
+ACT = {"none": 0, "relu": 1, "hswish": 2}
+
+
+def _act(v, act):
+    if act == "relu":
+        return torch.relu(v), (v > 0).double()
+    if act == "hswish":
+        f = v * torch.clamp(v + 3, 0, 6) / 6
+        d = torch.where(v < -3, torch.zeros_like(v), torch.where(v <= 3, (2 * v + 3) / 6, torch.ones_like(v)))
+        return f, d
+    return v, torch.ones_like(v)
+
+
+def _case(B, P, C, dtype, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    z = torch.randn(B, P, C, generator=g) * 1.5
+    dp = torch.randn(B, P, C, generator=g)
+    scale = torch.rand(C, generator=g) + 0.5
+    shift = torch.randn(C, generator=g) * 0.3
+    mean = torch.randn(C, generator=g) * 0.2
+    invstd = torch.rand(C, generator=g) + 0.5
+    gate = torch.rand(B, C, generator=g)
+    dpool = torch.randn(B, C, generator=g) * 0.1
+    z, dp = z.to(dtype), dp.to(dtype)
+    return [t.cuda().contiguous() for t in (z, dp, scale, shift, mean, invstd, gate, dpool)]
+
+
+def _reference(z, dp, scale, shift, mean, invstd, gate, dpool, act):
+    z, dp = z.double(), dp.double()
+    v = z * scale.double() + shift.double()
+    f, d = _act(v, act)
+    dgate = (dp * f).sum(1)
+    dy = (dp * gate.double()[:, None, :] + dpool.double()[:, None, :]) * d
+    s1 = dy.sum((0, 1))
+    s2 = (dy * (z - mean.double())).sum((0, 1)) * invstd.double()
+    return dgate, s1, s2
+
+
+def _close(got, want, rel):
+    scale = want.abs().max().item() + 1e-12
+    err = (got.double() - want).abs().max().item()
+    assert err <= rel * scale, (err, scale)
+
+
+# (B, P, C): several pixel slots per channel vector (shared-memory flush) / one owner per vector / more vectors than threads
+SHAPES = [(3, 37, 72), (5, 2000, 120), (2, 130, 960), (2, 50, 1536), (1, 1, 8), (4, 504, 672)]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("act", ["relu", "hswish"])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_se_bn_bwd_fused_reduce_matches_fp64_and_the_two_pass_kernels(shape, act, dtype):
+    B, P, C = shape
+    L = lib()
+    st = torch.cuda.current_stream().cuda_stream
+    z, dp, scale, shift, mean, invstd, gate, dpool = _case(B, P, C, dtype)
+    code = 1 if dtype == torch.bfloat16 else 0
+    want_dgate, want_s1, want_s2 = _reference(z, dp, scale, shift, mean, invstd, gate, dpool, act)
+    for parts in (1, 3, 7):
+        dgate = torch.zeros(B, C, device="cuda")
+        part = torch.full((parts, 4, B, C), float("nan"), device="cuda")       # every slice must be written
+        L.se_bn_bwd_reduce(dp.data_ptr(), z.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), ACT[act],
+                           dgate.data_ptr(), part.data_ptr(), parts, code, B, P, C, st)
+        s = torch.zeros(2, C, device="cuda", dtype=torch.float64)
+        L.se_bn_bwd_combine(part.data_ptr(), parts, gate.data_ptr(), dpool.data_ptr(), invstd.data_ptr(), B, C,
+                            s[0].data_ptr(), s[1].data_ptr(), st)
+        torch.cuda.synchronize()
+        assert torch.isfinite(part).all()
+        _close(dgate.cpu(), want_dgate.cpu(), 5e-5)
+        _close(s[0].cpu(), want_s1.cpu(), 5e-5)
+        _close(s[1].cpu(), want_s2.cpu(), 5e-5)
+    # the kernels it replaces, on the same data
+    dgate2 = torch.zeros(B, C, device="cuda")
+    L.se_bwd_reduce(dp.data_ptr(), z.data_ptr(), scale.data_ptr(), shift.data_ptr(), ACT[act], dgate2.data_ptr(), code, B, P, C, st)
+    s2 = torch.zeros(2, C, device="cuda", dtype=torch.float64)
+    L.bn_bwd_reduce(dp.data_ptr(), gate.data_ptr(), dpool.data_ptr(), z.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                    mean.data_ptr(), invstd.data_ptr(), ACT[act], code, B, P, C, s2[0].data_ptr(), s2[1].data_ptr(), st)
+    torch.cuda.synchronize()
+    _close(dgate2.cpu(), want_dgate.cpu(), 5e-5)
+    _close(s2[0].cpu(), want_s1.cpu(), 5e-5)
+    _close(s2[1].cpu(), want_s2.cpu(), 5e-5)

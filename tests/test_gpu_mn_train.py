@@ -15,10 +15,12 @@ from tests.util import build_model, golden, net_inputs
 pytestmark = pytest.mark.gpu
 
 
-def _run(tag, precision="fp32", gemm="auto"):
+def _run(tag, precision="fp32", gemm="auto", se_fused=None):
     g = golden(tag)
     model = build_model(tag, precision=precision).cuda().train()
     model.engine().gemm_impl = gemm
+    if se_fused is not None:
+        model.engine().se_fused = se_fused
     for m in model.modules():
         if isinstance(m, torch.nn.Dropout):
             m.p = 0.0
@@ -30,10 +32,12 @@ def _run(tag, precision="fp32", gemm="auto"):
     return g, model, logits, loss
 
 
+@pytest.mark.parametrize("se_fused", [False, True])
 @pytest.mark.parametrize("gemm", ["simt", "auto"])
 @pytest.mark.parametrize("tag", ["mn10", "mn04", "mn10_10s"])
-def test_mn_train_step_matches_reference_vectors(tag, gemm):
-    g, model, logits, loss = _run(tag, gemm=gemm)
+def test_mn_train_step_matches_reference_vectors(tag, gemm, se_fused):
+    """se_fused: the SE blocks' squeeze-excitation + BatchNorm-backward reduce in one pass (engine.se_fused) or two"""
+    g, model, logits, loss = _run(tag, gemm=gemm, se_fused=se_fused)
     norm_tol, samp_tol, loss_tol = (5e-3, 2e-2, 1e-5) if gemm == "simt" else (2e-2, 6e-2, 2e-5)
     assert np.abs(logits.detach().cpu().numpy() - g["train_logits"]).max() < 1e-3
     assert abs(loss.item() - float(g["train_loss"])) < loss_tol
