@@ -7,6 +7,7 @@
 // models/mn/model.py:125-133 and models/mn/block_types.py:140-170; SqueezeExcitation
 // models/mn/block_types.py:72-83.
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include <stdlib.h>
@@ -14,6 +15,7 @@
 namespace {
 
 constexpr int kThreads = 256;
+constexpr bool kPoolV2Default = false;   // eat_bn_act_pool: kernel generation used when EAT_POOL is not set
 
 // 4 consecutive channels <-> fp32 registers, for either storage type (16 B fp32 / 8 B bf16)
 template <typename T> struct Vec4IO;
@@ -514,6 +516,54 @@ __global__ void __launch_bounds__(kThreads) bn_act_pool_kernel(const T* __restri
   for (int c = threadIdx.x; c < C; c += kThreads) atomicAdd(pool + (size_t)b * C + c, smem[c] * mul);
 }
 
+// Second generation (the BatchNorm-backward reduce went the same way): same thread mapping, activation compile-time, the
+// two per-channel constants in registers, EIGHT pixels (fp32; four for bf16) = 128 bytes of loads in flight per thread.
+template <typename T, int ACT>
+__global__ void __launch_bounds__(kThreads, 3) bn_act_pool2_kernel(const T* __restrict__ z, const float* __restrict__ scale,
+                                                                   const float* __restrict__ shift,
+                                                                   float* __restrict__ pool, float mul, int P, int C) {
+  constexpr int V = Vec<T>::N;
+  constexpr int U = V == 4 ? 8 : 4;
+  extern __shared__ float smem[];
+  for (int i = threadIdx.x; i < C; i += kThreads) smem[i] = 0.f;
+  __syncthreads();
+  const int cv = C / V;
+  const int b = blockIdx.y;
+  const T* zb = z + (size_t)b * P * C;
+  const int tcv = cv < kThreads ? cv : kThreads;
+  const int ppb = kThreads / tcv;
+  const int slot = threadIdx.x / tcv;
+  if (slot < ppb) {
+    for (int cvi = threadIdx.x % tcv; cvi < cv; cvi += tcv) {
+      const int c0 = cvi * V;
+      float sc[V], sh[V], acc[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) { sc[k] = scale[c0 + k]; sh[k] = shift[c0 + k]; acc[k] = 0.f; }
+      const int step = gridDim.x * ppb;
+      int p = blockIdx.x * ppb + slot;
+      for (; p + (U - 1) * step < P; p += U * step) {
+        float v[U][V];
+#pragma unroll
+        for (int u = 0; u < U; ++u) Vec<T>::load(zb + (size_t)(p + u * step) * C + c0, v[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int k = 0; k < V; ++k) acc[k] += act_fwd(fmaf(v[u][k], sc[k], sh[k]), ACT);
+      }
+      for (; p < P; p += step) {
+        float v[V];
+        Vec<T>::load(zb + (size_t)p * C + c0, v);
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] += act_fwd(fmaf(v[k], sc[k], sh[k]), ACT);
+      }
+#pragma unroll
+      for (int k = 0; k < V; ++k) atomicAdd(&smem[c0 + k], acc[k]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kThreads) atomicAdd(pool + (size_t)b * C + c, smem[c] * mul);
+}
+
 // ------------------------------------------------------------------------------------------
 // Squeeze-excitation MLP: gate[b,:] = sigmoid(W2 relu(W1 (pool[b,:] * inv_count) + b1) + b2)
 // one CTA per sample; warp per output row (coalesced weight rows).
@@ -721,6 +771,25 @@ int eat_bn_act_pool(const void* z, const float* scale, const float* shift, int a
   if (gx < 1) gx = 1;
   dim3 grid(gx, B);
   size_t smem = (size_t)C * sizeof(float);
+  // EAT_POOL=v2|v1 selects the kernel generation (v2: eight pixels in flight, compile-time activation)
+  static const bool v2 = [] { const char* e = getenv("EAT_POOL"); return e != nullptr ? strcmp(e, "v2") == 0 : kPoolV2Default; }();
+  if (v2 && scale != nullptr && shift != nullptr && (act == EAT_ACT_NONE || act == EAT_ACT_RELU || act == EAT_ACT_HSWISH)) {
+    // more pixels per thread in flight: fewer, longer-lived CTAs (~12 per SM over the batch)
+    const int U = dtype == EAT_BF16 ? 4 : 8;
+    int g2 = ceil_div(P, ppb * U);
+    const int cap2 = max(1, (148 * 12) / B);
+    if (g2 > cap2) g2 = cap2;
+    if (g2 < 1) g2 = 1;
+    dim3 grid2(g2, B);
+#define EAT_POOL2(TT, ACT) bn_act_pool2_kernel<TT, ACT><<<grid2, kThreads, smem, st>>>((const TT*)z, scale, shift, pool, mul, P, C)
+#define EAT_POOL2_T(TT) do { if (act == EAT_ACT_RELU) EAT_POOL2(TT, EAT_ACT_RELU); else if (act == EAT_ACT_HSWISH) EAT_POOL2(TT, EAT_ACT_HSWISH); \
+                             else EAT_POOL2(TT, EAT_ACT_NONE); } while (0)
+    if (dtype == EAT_BF16) EAT_POOL2_T(__nv_bfloat16); else EAT_POOL2_T(float);
+#undef EAT_POOL2_T
+#undef EAT_POOL2
+    EAT_CHECK_LAUNCH();
+    return EAT_OK;
+  }
   if (dtype == EAT_BF16)
     bn_act_pool_kernel<__nv_bfloat16><<<grid, kThreads, smem, st>>>((const __nv_bfloat16*)z, scale, shift, act, pool, mul, P, C);
   else

@@ -90,3 +90,23 @@ def test_se_bn_bwd_fused_reduce_matches_fp64_and_the_two_pass_kernels(shape, act
     _close(dgate2.cpu(), want_dgate.cpu(), 5e-5)
     _close(s2[0].cpu(), want_s1.cpu(), 5e-5)
     _close(s2[1].cpu(), want_s2.cpu(), 5e-5)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("act", ["none", "relu", "hswish"])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_bn_act_pool_matches_fp64(shape, act, dtype):
+    """pool[b,c] += mul * sum_p act(z*scale+shift): the SE squeeze of a training step (block_types.py:73) and the global
+    average pool of the head (mn/model.py:216).  Runs whichever kernel generation EAT_POOL selects (default: see
+    kPoolV2Default in csrc/conv_kernels.cu); scripts/gpu_runs run the file under both."""
+    B, P, C = shape
+    L = lib()
+    st = torch.cuda.current_stream().cuda_stream
+    z, _, scale, shift, *_ = _case(B, P, C, dtype, seed=3)
+    code = 1 if dtype == torch.bfloat16 else 0
+    pool = torch.full((B, C), 0.25, device="cuda")
+    L.bn_act_pool(z.data_ptr(), scale.data_ptr(), shift.data_ptr(), ACT[act], pool.data_ptr(), 0.5, code, B, P, C, st)
+    torch.cuda.synchronize()
+    f, _ = _act(z.double() * scale.double() + shift.double(), act)
+    want = 0.25 + 0.5 * f.sum(1)
+    _close(pool.cpu(), want.cpu(), 5e-5)
