@@ -15,7 +15,7 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr bool kPoolV2Default = false;   // eat_bn_act_pool: kernel generation used when EAT_POOL is not set
+constexpr bool kPoolV2Default = true;    // eat_bn_act_pool: kernel generation used when EAT_POOL is not set (v2: 0.54 -> 0.45 ms per mn10 step)
 
 // 4 consecutive channels <-> fp32 registers, for either storage type (16 B fp32 / 8 B bf16)
 template <typename T> struct Vec4IO;

@@ -41,7 +41,8 @@ class _Layer:
     pass
 
 
-SE_FUSED_DEFAULT = "0"
+# measured (scripts/gpu_runs/r2_sefuse1.sh, mn10 B=256): 34.3 -> 33.76 ms/step; EAT_SE_FUSED=0 restores the two-pass route
+SE_FUSED_DEFAULT = "1"
 
 
 class _ZeroPool:
@@ -103,6 +104,7 @@ class MNEngine:
         # SE blocks: squeeze-excitation reduce + BatchNorm-backward reduce of the depthwise output in one pass over the two
         # expanded tensors (eat_se_bn_bwd_reduce / _combine) instead of two (eat_se_bwd_reduce, eat_bn_bwd_reduce)
         self.se_fused = os.environ.get("EAT_SE_FUSED", SE_FUSED_DEFAULT) == "1"
+        self.se_parts_per_sm = int(os.environ.get("EAT_SE_PARTS_PER_SM", "6"))
         self._fork = None
         self._se_scale = {}
         self._zero_pool = _ZeroPool()
@@ -514,8 +516,9 @@ class MNEngine:
             Sq = blk.se.fc1.out_features
             dgate = torch.zeros(B, blk.cexp, device=dev, dtype=torch.float32)
             if self.se_fused:
-                # ~12 CTAs per SM over the batch, at least ~16 pixels per slice
-                parts = max(1, min(32, (148 * 12) // B, (Po + 15) // 16))
+                # slices of a sample's pixels = CTAs per sample: ~EAT_SE_PARTS_PER_SM CTAs per SM over the batch, at least
+                # ~16 pixels per slice.  Every slice writes 4 x C partial sums, so few, long slices are preferred.
+                parts = max(1, min(32, (148 * self.se_parts_per_sm) // B, (Po + 15) // 16))
                 part = torch.empty(parts, 4, B, blk.cexp, device=dev, dtype=torch.float32)
                 L.se_bn_bwd_reduce(dp.data_ptr(), R["z2"].data_ptr(), R["sc2"][0].data_ptr(), R["sc2"][1].data_ptr(),
                                    R["sv2"][0].data_ptr(), blk.act, dgate.data_ptr(), part.data_ptr(), parts, dc, B, Po,

@@ -123,7 +123,8 @@ def test_native_batched_tagger_matches_reference_eatagger(tmp_path, monkeypatch,
     again = tagger.tag_waveform(wave, window_size=g["window_s"], hop_length=g["hop_s"])
     for a, b in zip(tags, again):
         assert [t["tag"] for t in a["tags"]] == [t["tag"] for t in b["tags"]]
-        assert max(abs(x["probability"] - y["probability"]) for x, y in zip(a["tags"], b["tags"])) <= 1e-6
+        # a different batch size picks different GEMM tiles / split factors: fp32 summation order, not values
+        assert max(abs(x["probability"] - y["probability"]) for x, y in zip(a["tags"], b["tags"])) <= 1e-5
 
 
 def test_ensemble_with_dymn_member_is_the_mean_of_the_golden_logits():
