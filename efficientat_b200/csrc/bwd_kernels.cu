@@ -936,6 +936,22 @@ int eat_dw_conv_dgrad(const void* dz, const float* wt, long long wt_bstride, con
   return launch_dw_bwd<float>(0, dz, wt, nullptr, xf, res, din, nullptr, B, F, T, C, k, stride, st, wt_bstride);
 }
 
+int eat_dw_conv_dgrad_bnred(const void* dz, const float* wt, const void* res, void* din, const void* z, const float* zscale,
+                            const float* zshift, const float* zmean, const float* zinvstd, int zact, double* s1, double* s2,
+                            int dtype, int B, int F, int T, int C, int k, int stride, cudaStream_t st) {
+  if (B == 0) return EAT_OK;
+  if (z == nullptr || zscale == nullptr || zshift == nullptr || zmean == nullptr || zinvstd == nullptr || s1 == nullptr ||
+      s2 == nullptr) {
+    eat_set_error("dw_conv_dgrad_bnred: z, its BatchNorm tables and the accumulators are required");
+    return EAT_ERR_ARG;
+  }
+  if (dtype != EAT_F32 || stride != 2 || (k != 3 && k != 5)) {
+    eat_set_error("dw_conv_dgrad_bnred: fp32 storage, stride 2, k in {3,5} only (use eat_dw_conv_dgrad + eat_bn_bwd_reduce)");
+    return EAT_ERR_UNSUPPORTED;
+  }
+  return dw_dgrad2_slide_launch(dz, wt, 0, res, din, dtype, B, F, T, C, k, st, z, zscale, zshift, zmean, zinvstd, zact, s1, s2);
+}
+
 int eat_dw_conv_wgrad(const void* dz, const void* in, const float* in_scale, const float* in_shift, int in_act,
                       float* dw, long long dw_bstride, int dtype, int B, int F, int T, int C, int k, int stride,
                       cudaStream_t st) {

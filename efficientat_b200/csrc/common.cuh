@@ -111,8 +111,11 @@ int dw_slide_launch(const void* in, const float* wt, void* out, int dtype, int B
 int dw_wgrad_slide_launch(const void* dz, const void* in, InXform xf, float* dw, long long dw_bstride, int dtype, int B,
                           int F, int Tn, int C, int k, int stride, cudaStream_t st);
 
+// z != nullptr: BatchNorm-backward reduce of the layer behind din in the epilogue (fp32 storage; see Dg2Args in dw_slide.cu)
 int dw_dgrad2_slide_launch(const void* dz, const float* wt, long long wt_bstride, const void* res, void* din, int dtype,
-                           int B, int F, int Tn, int C, int k, cudaStream_t st);
+                           int B, int F, int Tn, int C, int k, cudaStream_t st, const void* z = nullptr,
+                           const float* zscale = nullptr, const float* zshift = nullptr, const float* zmean = nullptr,
+                           const float* zinvstd = nullptr, int zact = 0, double* s1 = nullptr, double* s2 = nullptr);
 
 // CUDA-core weight gradient for narrow 1x1 convolutions (wgrad_narrow.cu); EAT_ERR_UNSUPPORTED = shape out of range
 int wgrad_narrow_launch(const float* G, const float* A, float* dW, long long M, int N, int K, const float* in_scale,

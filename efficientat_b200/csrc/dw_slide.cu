@@ -817,9 +817,20 @@ struct Dg2Args {
   int cvc, chunks, seg_rows;   // seg_rows counts row PAIRS
   int per_sample;
   int depth;                   // prefetch ring depth in dz rows (RING kernels)
+  // RED kernels: din is the upstream gradient of a BatchNorm + activation whose raw input z has din's shape; the
+  // BatchNorm-backward reduce (s1 += sum g, s2 += invstd * sum g * (z - mean), g = din * act'(z*scale+shift)) is taken
+  // in the epilogue, while the din values are still in registers -- the separate reduce pass would read din and z again
+  const void* z;
+  const float* zscale;
+  const float* zshift;
+  const float* zmean;
+  const float* zinvstd;
+  int zact;
+  double* s1;
+  double* s2;
 };
 
-template <typename T, int K, int MINB, bool RING>
+template <typename T, int K, int MINB, bool RING, bool RED = false>
 __global__ void __launch_bounds__(kST, MINB) dw_dgrad2_slide_kernel(const Dg2Args a) {
   constexpr int V = Vec<T>::N;
   constexpr int Q = 4, PAD = (K - 1) / 2, KK = K * K;
@@ -834,32 +845,48 @@ __global__ void __launch_bounds__(kST, MINB) dw_dgrad2_slide_kernel(const Dg2Arg
   const int cc = ncv * V;
   float* s_w = smem;                             // [KK][cc]
   const int tid = threadIdx.x;
-  const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(s_w + KK * a.cvc * V) + (uint32_t)tid * 16u;   // [depth][NDZ][kST] x 16 B
-  const unsigned char* ringp = reinterpret_cast<const unsigned char*>(s_w + KK * a.cvc * V) + tid * 16;
+  const int cst = a.cvc * V;                     // channel stride of the per-CTA tables
+  float* s_bn = s_w + KK * cst;                  // RED: [3][cst] scale, shift, mean of the BatchNorm behind din
+  float* s_red = s_bn + 3 * cst;                 // RED: [2][cst] CTA partial sums
+  float* s_end = RED ? s_red + 2 * cst : s_bn;   // the prefetch ring follows the tables
+  const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(s_end) + (uint32_t)tid * 16u;   // [depth][NDZ][kST] x 16 B
+  const unsigned char* ringp = reinterpret_cast<const unsigned char*>(s_end) + tid * 16;
   {
     const float* wsrc = a.wt + (a.per_sample ? (size_t)blockIdx.y * a.wt_bstride : 0) + (size_t)cv0 * V;
     for (int i = tid; i < KK * cc; i += kST) {
       const int tap = i / cc, c = i - tap * cc;
       s_w[i] = __ldg(wsrc + (size_t)tap * C + c);
     }
+    if (RED) {
+      for (int c = tid; c < cc; c += kST) {
+        const int cg = cv0 * V + c;
+        s_bn[c] = __ldg(a.zscale + cg); s_bn[cst + c] = __ldg(a.zshift + cg); s_bn[2 * cst + c] = __ldg(a.zmean + cg);
+        s_red[c] = 0.f; s_red[cst + c] = 0.f;
+      }
+    }
   }
   __syncthreads();
   const int ppb = kST / ncv;
   const int cvl = tid % ncv, slot = tid / ncv;
-  if (slot >= ppb) return;
+  if (!RED && slot >= ppb) return;               // RED: idle threads still take part in the final CTA reduction
   const int c0 = (cv0 + cvl) * V;
   const float* wl = s_w + cvl * V;
+  float lsum[V], lsq[V];                         // RED: this thread's share of sum g, sum g * (z - mean)
+#pragma unroll
+  for (int i = 0; i < V; ++i) { lsum[i] = 0.f; lsq[i] = 0.f; }
   const int pairs = (F + 1) / 2;
   const int strips = ceil_div(Tn, Q), segs = ceil_div(pairs, a.seg_rows), units = strips * segs;
   long long g = a.per_sample ? (long long)blockIdx.y * units + grp * ppb + slot : ((long long)blockIdx.y * groups + grp) * ppb + slot;
   const long long gend = a.per_sample ? (long long)(blockIdx.y + 1) * units : (long long)a.B * units;
   const long long gstep = a.per_sample ? (long long)groups * ppb : (long long)gridDim.y * groups * ppb;
+  if (RED && slot >= ppb) g = gend;
   for (; g < gend; g += gstep) {
     const int b = (int)(g / units);
     const int u = (int)(g - (long long)b * units);
     const T* dzb = reinterpret_cast<const T*>(a.dz) + (size_t)b * Fo * To * C + c0;
     T* dinb = reinterpret_cast<T*>(a.din) + (size_t)b * F * Tn * C + c0;
     const T* resb = a.res != nullptr ? reinterpret_cast<const T*>(a.res) + (size_t)b * F * Tn * C + c0 : nullptr;
+    const T* zb = RED ? reinterpret_cast<const T*>(a.z) + (size_t)b * F * Tn * C + c0 : nullptr;
     const int seg = u / strips, strip = u - seg * strips;
     const int m_a = seg * a.seg_rows;
     const int npair = min(a.seg_rows, pairs - m_a);
@@ -974,25 +1001,78 @@ __global__ void __launch_bounds__(kST, MINB) dw_dgrad2_slide_kernel(const Dg2Arg
               for (int i = 0; i < V; ++i) acc[q][i] += rv[i];
             }
             Vec<T>::store(dinb + off, acc[q]);
+            if (RED) {
+              float zv[V];
+              Vec<T>::load(zb + off, zv);
+              const float* bn = s_bn + cvl * V;
+#pragma unroll
+              for (int i = 0; i < V; ++i) {
+                const float gd = acc[q][i] * act_bwd(fmaf(zv[i], bn[i], bn[cst + i]), a.zact);
+                lsum[i] += gd;
+                lsq[i] = fmaf(gd, zv[i] - bn[2 * cst + i], lsq[i]);
+              }
+            }
           }
         }
       }
     }
   }
+  if (RED) {
+    if (slot < ppb) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) { atomicAdd(&s_red[cvl * V + i], lsum[i]); atomicAdd(&s_red[cst + cvl * V + i], lsq[i]); }
+    }
+    __syncthreads();
+    for (int c = tid; c < cc; c += kST) {
+      const int cg = cv0 * V + c;
+      atomicAdd(a.s1 + cg, (double)s_red[c]);
+      atomicAdd(a.s2 + cg, (double)s_red[cst + c] * (double)__ldg(a.zinvstd + cg));
+    }
+  }
 }
+
+// resident CTAs per SM of the RED variants (the epilogue needs ~16 more registers than the plain kernels' 104 / 160)
+constexpr int kDg2RedMinB3 = 4, kDg2RedMinB5 = 3;
 
 template <typename T>
 int launch_dg2_slide(Dg2Args a, int k, cudaStream_t st) {
   constexpr int V = Vec<T>::N;
   const int cv = a.C / V;
-  const int minb = k == 3 ? 4 : 3;
+  const int minb = a.z != nullptr ? (k == 3 ? kDg2RedMinB3 : kDg2RedMinB5) : (k == 3 ? 4 : 3);
   a.per_sample = a.wt_bstride != 0 ? 1 : 0;
   const int pairs = (a.F + 1) / 2;
   const SlidePlan pl = plan_slide(a.B, pairs, a.Tn, cv, V, 4, 1, (k + 1) / 2, minb, a.per_sample != 0);
   a.chunks = pl.chunks; a.cvc = pl.cvc; a.seg_rows = pl.seg_rows;
   dim3 grid(pl.chunks * pl.groups, pl.gy);
-  const size_t smem = (size_t)k * k * a.cvc * V * sizeof(float);
   constexpr int NDZ3 = 4 / 2 + 1 / 2 + 1, NDZ5 = 4 / 2 + 2 / 2 + 1;
+  if (a.z != nullptr) {
+    // BatchNorm-backward reduce in the epilogue (fp32 storage only): five more per-channel tables in shared memory
+    if constexpr (std::is_same<T, float>::value) {
+      const size_t smem_r = (size_t)(k * k + 5) * a.cvc * V * sizeof(float);
+      static unsigned long long r3 = 0, r5 = 0, r5n = 0;
+      if (k == 3) {
+        a.depth = 0;
+        if (int rc = eat_opt_in_smem(dw_dgrad2_slide_kernel<T, 3, kDg2RedMinB3, false, true>, 64 * 1024, r3)) return rc;
+        dw_dgrad2_slide_kernel<T, 3, kDg2RedMinB3, false, true><<<grid, kST, smem_r, st>>>(a);
+      } else {
+        const size_t slot = (size_t)NDZ5 * kST * 16;
+        a.depth = ring_depth((size_t)(227 * 1024) / kDg2RedMinB5 - 1024, smem_r, slot, 2);
+        if (a.depth > 0) {
+          if (int rc = eat_opt_in_smem(dw_dgrad2_slide_kernel<T, 5, kDg2RedMinB5, true, true>, 200 * 1024, r5)) return rc;
+          dw_dgrad2_slide_kernel<T, 5, kDg2RedMinB5, true, true><<<grid, kST, smem_r + a.depth * slot, st>>>(a);
+        } else {
+          if (int rc = eat_opt_in_smem(dw_dgrad2_slide_kernel<T, 5, kDg2RedMinB5, false, true>, 64 * 1024, r5n)) return rc;
+          dw_dgrad2_slide_kernel<T, 5, kDg2RedMinB5, false, true><<<grid, kST, smem_r, st>>>(a);
+        }
+      }
+      EAT_CHECK_LAUNCH();
+      return EAT_OK;
+    } else {
+      eat_set_error("dw dgrad with BatchNorm reduce: fp32 storage only");
+      return EAT_ERR_UNSUPPORTED;
+    }
+  }
+  const size_t smem = (size_t)k * k * a.cvc * V * sizeof(float);
   static unsigned long long m3 = 0, m5 = 0, m5n = 0;
   if (k == 3) {
     const size_t slot = (size_t)NDZ3 * kST * 16;
@@ -1061,13 +1141,16 @@ int dw_wgrad_slide_launch(const void* dz, const void* in, InXform xf, float* dw,
 }
 
 int dw_dgrad2_slide_launch(const void* dz, const float* wt, long long wt_bstride, const void* res, void* din, int dtype,
-                           int B, int F, int Tn, int C, int k, cudaStream_t st) {
+                           int B, int F, int Tn, int C, int k, cudaStream_t st, const void* z, const float* zscale,
+                           const float* zshift, const float* zmean, const float* zinvstd, int zact, double* s1,
+                           double* s2) {
   const int V = dtype == EAT_BF16 ? 8 : 4;
   if (C % V != 0) { eat_set_error("dw dgrad: channels must be a multiple of the vector width"); return EAT_ERR_ARG; }
   if (k != 3 && k != 5) { eat_set_error("dw dgrad slide: k in {3,5} only"); return EAT_ERR_UNSUPPORTED; }
   const int pad = (k - 1) / 2;
   Dg2Args a;
   a.dz = dz; a.wt = wt; a.wt_bstride = wt_bstride; a.res = res; a.din = din;
+  a.z = z; a.zscale = zscale; a.zshift = zshift; a.zmean = zmean; a.zinvstd = zinvstd; a.zact = zact; a.s1 = s1; a.s2 = s2;
   a.B = B; a.F = F; a.Tn = Tn; a.C = C;
   a.Fo = (F + 2 * pad - k) / 2 + 1;
   a.To = (Tn + 2 * pad - k) / 2 + 1;

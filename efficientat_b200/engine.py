@@ -45,6 +45,9 @@ class _Layer:
 SE_FUSED_DEFAULT = "1"
 
 
+DGRAD_BNRED_DEFAULT = "0"
+
+
 class _ZeroPool:
     """fp64 accumulators for BatchNorm statistics, carved from chunks that are zeroed with ONE fill each
     (a training step needs ~100 small zeroed buffers; one launch per buffer showed up as 250 tiny kernels)."""
@@ -105,6 +108,9 @@ class MNEngine:
         # expanded tensors (eat_se_bn_bwd_reduce / _combine) instead of two (eat_se_bwd_reduce, eat_bn_bwd_reduce)
         self.se_fused = os.environ.get("EAT_SE_FUSED", SE_FUSED_DEFAULT) == "1"
         self.se_parts_per_sm = int(os.environ.get("EAT_SE_PARTS_PER_SM", "6"))
+        # stride-2 blocks: the BatchNorm-backward reduce of the expand stage inside the depthwise data-gradient kernel that
+        # produces its upstream gradient (eat_dw_conv_dgrad_bnred), fp32 storage
+        self.dgrad_bnred = os.environ.get("EAT_DGRAD_BNRED", DGRAD_BNRED_DEFAULT) == "1"
         self._fork = None
         self._se_scale = {}
         self._zero_pool = _ZeroPool()
@@ -551,12 +557,21 @@ class MNEngine:
                                          G[blk.dw[0].weight].data_ptr(), 0, dc, B, Fi, Ti, blk.cexp, blk.k, blk.stride,
                                          _stream()), dz2)
         da1 = torch.empty_like(dw_in)
-        # without an expand stage the depthwise input IS the block input: fold the residual gradient in
-        L.dw_conv_dgrad(dz2.data_ptr(), R["wt"].data_ptr(), 0, _ptr(dy) if (blk.res and not has_exp) else 0,
-                        da1.data_ptr(), dc, B, Fi, Ti, blk.cexp, blk.k, blk.stride, st)
+        sums1 = None
+        if has_exp and self.dgrad_bnred and blk.stride == 2 and dc == 0 and blk.k in (3, 5):
+            # the expand BatchNorm's reduce pass rides in the epilogue of the kernel that produces its upstream gradient
+            sums1 = self._zero_pool.take(2, blk.cexp, dev)
+            L.dw_conv_dgrad_bnred(dz2.data_ptr(), R["wt"].data_ptr(), 0, da1.data_ptr(), R["z1"].data_ptr(),
+                                  R["sc1"][0].data_ptr(), R["sc1"][1].data_ptr(), R["sv1"][0].data_ptr(),
+                                  R["sv1"][1].data_ptr(), blk.act, sums1[0].data_ptr(), sums1[1].data_ptr(), dc, B, Fi, Ti,
+                                  blk.cexp, blk.k, blk.stride, st)
+        else:
+            # without an expand stage the depthwise input IS the block input: fold the residual gradient in
+            L.dw_conv_dgrad(dz2.data_ptr(), R["wt"].data_ptr(), 0, _ptr(dy) if (blk.res and not has_exp) else 0,
+                            da1.data_ptr(), dc, B, Fi, Ti, blk.cexp, blk.k, blk.stride, st)
         if has_exp:
             dz1 = self._bn_bwd(da1, None, None, R["z1"], R["sc1"], R["sv1"], blk.act, B, Pi, blk.cexp,
-                               G[blk.expand[1].weight], G[blk.expand[1].bias], dev)
+                               G[blk.expand[1].weight], G[blk.expand[1].bias], dev, sums=sums1)
             fork.run(lambda: self._wgrad(dz1, R["inp"], G[blk.expand[0].weight], None, B * Pi, blk.cexp, blk.cin), dz1)
             dinp = torch.empty_like(R["inp"])
             self._gemm(dz1, blk.expand[0].weight, dinp, B * Pi, blk.cin, blk.cexp, w_trans=True,

@@ -265,6 +265,14 @@ int eat_dw_conv_dgrad(const void* dz, const float* wt, long long wt_bstride, con
                       int F, int T, int C, int k, int stride, cudaStream_t stream);
 int eat_dw_conv_dgrad_s1(const void* dz, const float* wt, long long wt_bstride, const void* res, void* din, int dtype,
                          int B, int F, int T, int C, int k, cudaStream_t stream);   /* stride-1 fast path */
+/* Stride-2 data gradient whose output din [B,F,T,C] is the upstream gradient of a BatchNorm + activation with raw input
+ * z [B,F,T,C] (the expand stage of an InvertedResidual, block_types.py:140-147): the BatchNorm-backward reduce
+ * (s1[c] += sum g, s2[c] += invstd[c] * sum g*(z-mean[c]), g = din * act'(z*scale+shift) -- what eat_bn_bwd_reduce(gA = din)
+ * yields) is taken in the epilogue while din is still in registers.  fp32 storage, k in {3,5}; anything else returns
+ * EAT_ERR_UNSUPPORTED and the caller runs eat_dw_conv_dgrad + eat_bn_bwd_reduce. */
+int eat_dw_conv_dgrad_bnred(const void* dz, const float* wt, const void* res, void* din, const void* z, const float* zscale,
+                            const float* zshift, const float* zmean, const float* zinvstd, int zact, double* s1, double* s2,
+                            int dtype, int B, int F, int T, int C, int k, int stride, cudaStream_t stream);
 int eat_dw_conv_wgrad(const void* dz, const void* in, const float* in_scale, const float* in_shift, int in_act,
                       float* dw, long long dw_bstride, int dtype, int B, int F, int T, int C, int k, int stride,
                       cudaStream_t stream);   /* wt_bstride / dw_bstride: floats between per-sample tables (0: shared) */

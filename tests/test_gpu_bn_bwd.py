@@ -110,3 +110,47 @@ def test_bn_act_pool_matches_fp64(shape, act, dtype):
     f, _ = _act(z.double() * scale.double() + shift.double(), act)
     want = 0.25 + 0.5 * f.sum(1)
     _close(pool.cpu(), want.cpu(), 5e-5)
+
+
+@pytest.mark.parametrize("act", ["relu", "hswish"])
+@pytest.mark.parametrize("shape", [(3, 9, 21, 72, 5), (2, 16, 50, 64, 3), (2, 8, 13, 672, 5), (1, 2, 3, 8, 3), (2, 64, 100, 24, 3)])
+def test_dw_dgrad_stride2_with_bn_reduce_epilogue(shape, act):
+    """eat_dw_conv_dgrad_bnred: the same din as eat_dw_conv_dgrad, bit for bit, and the sums eat_bn_bwd_reduce(gA = din)
+    yields (also checked against fp64 torch) -- the expand-stage BatchNorm of a stride-2 InvertedResidual."""
+    B, F, T, C, k = shape
+    L = lib()
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(11)
+    pad = (k - 1) // 2
+    Fo, To = (F + 2 * pad - k) // 2 + 1, (T + 2 * pad - k) // 2 + 1
+    dz = torch.randn(B, Fo, To, C, generator=g).cuda()
+    w = (torch.randn(C, 1, k, k, generator=g) * 0.3).cuda()
+    z = (torch.randn(B, F, T, C, generator=g) * 1.5).cuda()
+    scale, shift = (torch.rand(C, generator=g) + 0.5).cuda(), (torch.randn(C, generator=g) * 0.3).cuda()
+    mean, invstd = (torch.randn(C, generator=g) * 0.2).cuda(), (torch.rand(C, generator=g) + 0.5).cuda()
+    wt = torch.empty(k * k, C, device="cuda")
+    L.dw_repack(w.data_ptr(), wt.data_ptr(), C, k, st)
+    din0 = torch.empty(B, F, T, C, device="cuda")
+    L.dw_conv_dgrad(dz.data_ptr(), wt.data_ptr(), 0, 0, din0.data_ptr(), 0, B, F, T, C, k, 2, st)
+    s0 = torch.zeros(2, C, device="cuda", dtype=torch.float64)
+    L.bn_bwd_reduce(din0.data_ptr(), 0, 0, z.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
+                    invstd.data_ptr(), ACT[act], 0, B, F * T, C, s0[0].data_ptr(), s0[1].data_ptr(), st)
+    din1 = torch.full((B, F, T, C), float("nan"), device="cuda")
+    s1 = torch.zeros(2, C, device="cuda", dtype=torch.float64)
+    L.dw_conv_dgrad_bnred(dz.data_ptr(), wt.data_ptr(), 0, din1.data_ptr(), z.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                          mean.data_ptr(), invstd.data_ptr(), ACT[act], s1[0].data_ptr(), s1[1].data_ptr(), 0, B, F, T, C, k, 2, st)
+    torch.cuda.synchronize()
+    assert torch.equal(din0, din1)
+    # fp64 reference of the data gradient (conv_transpose of the depthwise kernel) and of the reduce
+    ref = torch.nn.functional.conv_transpose2d(dz.double().permute(0, 3, 1, 2), w.double(), stride=2, padding=pad, groups=C,
+                                               output_padding=(F - ((Fo - 1) * 2 - 2 * pad + k), T - ((To - 1) * 2 - 2 * pad + k)))
+    ref = ref.permute(0, 2, 3, 1)
+    assert (din1.double() - ref).abs().max().item() <= 1e-5 * (ref.abs().max().item() + 1e-12)
+    v = z.double() * scale.double() + shift.double()
+    _, d = _act(v, act)
+    gd = ref * d
+    want1 = gd.sum((0, 1, 2))
+    want2 = (gd * (z.double() - mean.double())).sum((0, 1, 2)) * invstd.double()
+    for got in (s0, s1):
+        _close(got[0].cpu(), want1.cpu(), 5e-5)
+        _close(got[1].cpu(), want2.cpu(), 5e-5)

@@ -15,12 +15,16 @@ from tests.util import build_model, golden, net_inputs
 pytestmark = pytest.mark.gpu
 
 
-def _run(tag, precision="fp32", gemm="auto", se_fused=None):
+# which BatchNorm-backward reduce passes ride inside another kernel (engine.se_fused, engine.dgrad_bnred)
+FUSION = {"two_pass": (False, False), "se_fused": (True, False), "all_fused": (True, True)}
+
+
+def _run(tag, precision="fp32", gemm="auto", fusion=None):
     g = golden(tag)
     model = build_model(tag, precision=precision).cuda().train()
     model.engine().gemm_impl = gemm
-    if se_fused is not None:
-        model.engine().se_fused = se_fused
+    if fusion is not None:
+        model.engine().se_fused, model.engine().dgrad_bnred = FUSION[fusion]
     for m in model.modules():
         if isinstance(m, torch.nn.Dropout):
             m.p = 0.0
@@ -32,12 +36,13 @@ def _run(tag, precision="fp32", gemm="auto", se_fused=None):
     return g, model, logits, loss
 
 
-@pytest.mark.parametrize("se_fused", [False, True])
+@pytest.mark.parametrize("fusion", list(FUSION))
 @pytest.mark.parametrize("gemm", ["simt", "auto"])
 @pytest.mark.parametrize("tag", ["mn10", "mn04", "mn10_10s"])
-def test_mn_train_step_matches_reference_vectors(tag, gemm, se_fused):
-    """se_fused: the SE blocks' squeeze-excitation + BatchNorm-backward reduce in one pass (engine.se_fused) or two"""
-    g, model, logits, loss = _run(tag, gemm=gemm, se_fused=se_fused)
+def test_mn_train_step_matches_reference_vectors(tag, gemm, fusion):
+    """fusion: the SE blocks' squeeze-excitation + BatchNorm-backward reduce in one pass (engine.se_fused) and the expand
+    BatchNorm's reduce inside the stride-2 depthwise data-gradient kernel (engine.dgrad_bnred), or separate passes"""
+    g, model, logits, loss = _run(tag, gemm=gemm, fusion=fusion)
     norm_tol, samp_tol, loss_tol = (5e-3, 2e-2, 1e-5) if gemm == "simt" else (2e-2, 6e-2, 2e-5)
     assert np.abs(logits.detach().cpu().numpy() - g["train_logits"]).max() < 1e-3
     assert abs(loss.item() - float(g["train_loss"])) < loss_tol
