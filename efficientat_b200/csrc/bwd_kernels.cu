@@ -13,6 +13,7 @@
 namespace {
 
 constexpr int kThreads = 256;
+constexpr bool kBnApplyV2Default = false;   // eat_bn_bwd_apply: kernel generation used when EAT_BN_APPLY is not set
 
 struct BnCtx {
   const float* scale;   // gamma * invstd      [C]
@@ -223,6 +224,69 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(
       Vec<T>::load(z + o0, z0);
       if (gA != nullptr) Vec<T>::load(gA + o0, g0);
       one(z0, g0, o0);
+    }
+  }
+}
+
+// Second generation of the apply pass (as bn_bwd_reduce2_kernel for the reduce): activation and gradient composition are
+// compile-time (ACT, GM: 0 g = gA; 1 g = gA * gate + dpool; 2 g = dpool), the per-channel constants are folded into four
+//   dz = scale * (dy - c1 - xhat * c2) = scale * dy + alpha * z + beta,   alpha = -scale*c2*invstd,  beta = -scale*c1 - alpha*mean
+// and FOUR pixels (two for bf16) = eight 16-byte loads are in flight per thread before the first use.
+template <typename T, int ACT, int GM>
+__global__ void __launch_bounds__(kThreads, 3) bn_bwd_apply2_kernel(
+    const T* __restrict__ gA, const float* __restrict__ gate, const float* __restrict__ dpool,
+    const T* __restrict__ z, BnCtx bn, const float* __restrict__ c1, const float* __restrict__ c2,
+    T* __restrict__ dz, int B, int P, int C) {
+  constexpr int V = Vec<T>::N;
+  constexpr int U = V == 4 ? 4 : 2;
+  const int cv = C / V;
+  const int tcv = cv < kThreads ? cv : kThreads;
+  const int ppb = kThreads / tcv;
+  const int slot = threadIdx.x / tcv;
+  const int b = blockIdx.y;
+  if (slot >= ppb) return;
+  for (int cvi = threadIdx.x % tcv; cvi < cv; cvi += tcv) {
+    const int c0 = cvi * V;
+    float sc[V], sh[V], al[V], be[V], gt[V], dp[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const int c = c0 + k;
+      sc[k] = bn.scale[c]; sh[k] = bn.shift[c];
+      al[k] = -sc[k] * c2[c] * bn.invstd[c];
+      be[k] = -sc[k] * c1[c] - al[k] * bn.mean[c];
+      gt[k] = (GM == 1 && gate != nullptr) ? gate[(size_t)b * C + c] : 1.f;
+      dp[k] = (GM != 0 && dpool != nullptr) ? dpool[(size_t)b * C + c] : 0.f;
+    }
+    const size_t base = (size_t)b * P * C + c0;
+    const int step = gridDim.x * ppb;
+    auto one = [&](const float (&zv)[V], const float (&gv)[V], size_t off) {
+      float o[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        float g = GM == 0 ? gv[k] : (GM == 1 ? fmaf(gv[k], gt[k], dp[k]) : dp[k]);
+        if (ACT != EAT_ACT_NONE) g *= act_bwd(fmaf(zv[k], sc[k], sh[k]), ACT);
+        o[k] = fmaf(sc[k], g, fmaf(al[k], zv[k], be[k]));
+      }
+      Vec<T>::store(dz + off, o);
+    };
+    int p = blockIdx.x * ppb + slot;
+    for (; p + (U - 1) * step < P; p += U * step) {
+      float zz[U][V], gg[U][V];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t o = base + (size_t)(p + u * step) * C;
+        Vec<T>::load(z + o, zz[u]);
+        if (GM != 2) Vec<T>::load(gA + o, gg[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) one(zz[u], gg[u], base + (size_t)(p + u * step) * C);
+    }
+    for (; p < P; p += step) {
+      const size_t o = base + (size_t)p * C;
+      float z0[V], g0[V];
+      Vec<T>::load(z + o, z0);
+      if (GM != 2) Vec<T>::load(gA + o, g0);
+      one(z0, g0, o);
     }
   }
 }
@@ -845,6 +909,26 @@ int eat_bn_bwd_apply(const void* gA, const float* gate, const float* dpool, cons
   const int V = dtype == EAT_BF16 ? 8 : 4;
   if (C % V != 0) { eat_set_error("bn_bwd_apply: channels must be a multiple of the vector width"); return EAT_ERR_ARG; }
   const int cv = C / V, tcv = cv < kThreads ? cv : kThreads, ppb = kThreads / tcv;
+  // EAT_BN_APPLY=v2|v1 selects the kernel generation
+  static const bool v2 = [] { const char* e = getenv("EAT_BN_APPLY"); return e != nullptr ? strcmp(e, "v2") == 0 : kBnApplyV2Default; }();
+  if (v2 && (act == EAT_ACT_NONE || act == EAT_ACT_RELU || act == EAT_ACT_HSWISH)) {
+    // ~12 CTAs per SM in total (3 resident at a time), at least 4 pixels per thread
+    int g2 = ceil_div(P, ppb * 4);
+    const int cap2 = max(1, (148 * 12) / max(B, 1));
+    if (g2 > cap2) g2 = cap2;
+    dim3 grid2(g2 < 1 ? 1 : g2, B);
+    const int gm = gA == nullptr ? 2 : ((gate != nullptr || dpool != nullptr) ? 1 : 0);
+#define EAT_APP(TT, ACT, GM) bn_bwd_apply2_kernel<TT, ACT, GM><<<grid2, kThreads, 0, st>>>((const TT*)gA, gate, dpool, (const TT*)z, bn, c1, c2, (TT*)dz, B, P, C)
+#define EAT_APP_A(TT, ACT) do { if (gm == 0) EAT_APP(TT, ACT, 0); else if (gm == 1) EAT_APP(TT, ACT, 1); else EAT_APP(TT, ACT, 2); } while (0)
+#define EAT_APP_T(TT) do { if (act == EAT_ACT_RELU) EAT_APP_A(TT, EAT_ACT_RELU); else if (act == EAT_ACT_HSWISH) EAT_APP_A(TT, EAT_ACT_HSWISH); \
+                           else EAT_APP_A(TT, EAT_ACT_NONE); } while (0)
+    if (dtype == EAT_BF16) EAT_APP_T(__nv_bfloat16); else EAT_APP_T(float);
+#undef EAT_APP_T
+#undef EAT_APP_A
+#undef EAT_APP
+    EAT_CHECK_LAUNCH();
+    return EAT_OK;
+  }
   // ~16 CTAs per SM in total, at least 2 pixels per thread
   int gx = ceil_div(P, 2 * ppb);
   const int cap = max(1, (148 * 16) / max(B, 1));

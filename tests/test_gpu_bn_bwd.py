@@ -154,3 +154,41 @@ def test_dw_dgrad_stride2_with_bn_reduce_epilogue(shape, act):
     for got in (s0, s1):
         _close(got[0].cpu(), want1.cpu(), 5e-5)
         _close(got[1].cpu(), want2.cpu(), 5e-5)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("compose", ["plain", "gate_dpool", "dpool_only"])
+@pytest.mark.parametrize("act", ["none", "relu", "hswish"])
+@pytest.mark.parametrize("shape", [(3, 37, 72), (2, 130, 960), (2, 50, 1536), (1, 1, 8), (5, 2001, 16)])
+def test_bn_bwd_apply_matches_fp64(shape, act, compose, dtype):
+    """dz = scale * (dy - c1 - xhat * c2), dy = (gA * gate + dpool) * act'(z*scale+shift): pass 2 of the BatchNorm backward
+    (autograd of nn.BatchNorm2d in training mode followed by Hardswish / ReLU).  Runs whichever kernel generation
+    EAT_BN_APPLY selects (default: kBnApplyV2Default in csrc/bwd_kernels.cu)."""
+    B, P, C = shape
+    L = lib()
+    st = torch.cuda.current_stream().cuda_stream
+    z, gA, scale, shift, mean, invstd, gate, dpool = _case(B, P, C, dtype, seed=5)
+    g = torch.Generator().manual_seed(9)
+    c1, c2 = (torch.randn(C, generator=g) * 0.1).cuda(), (torch.randn(C, generator=g) * 0.1).cuda()
+    code = 1 if dtype == torch.bfloat16 else 0
+    p = lambda t: t.data_ptr()
+    use_gA = compose != "dpool_only"
+    use_gate = compose == "gate_dpool"
+    use_dp = compose != "plain"
+    dz = torch.full((B, P, C), float("nan"), device="cuda", dtype=dtype)
+    L.bn_bwd_apply(p(gA) if use_gA else 0, p(gate) if use_gate else 0, p(dpool) if use_dp else 0, p(z), p(scale), p(shift),
+                   p(mean), p(invstd), ACT[act], p(c1), p(c2), p(dz), code, B, P, C, st)
+    torch.cuda.synchronize()
+    zd = z.double()
+    _, d = _act(zd * scale.double() + shift.double(), act)
+    gg = gA.double() if use_gA else torch.zeros_like(zd)
+    if use_gate:
+        gg = gg * gate.double()[:, None, :]
+    if use_dp:
+        gg = gg + dpool.double()[:, None, :]
+    dy = gg * d
+    xhat = (zd - mean.double()) * invstd.double()
+    want = scale.double() * (dy - c1.double() - xhat * c2.double())
+    tol = 1e-5 if dtype == torch.float32 else 1e-2        # bf16: the stored result is rounded to 8 bits of mantissa
+    assert torch.isfinite(dz.float()).all()
+    _close(dz.cpu(), want.cpu(), tol)
