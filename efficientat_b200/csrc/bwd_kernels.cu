@@ -13,7 +13,7 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr bool kBnApplyV2Default = false;   // eat_bn_bwd_apply: kernel generation used when EAT_BN_APPLY is not set
+constexpr bool kBnApplyV2Default = true;    // eat_bn_bwd_apply: kernel generation used when EAT_BN_APPLY is not set (v2: 6.19 -> 5.42 ms per mn10 step)
 
 struct BnCtx {
   const float* scale;   // gamma * invstd      [C]
