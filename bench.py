@@ -334,6 +334,22 @@ def algo_bytes(name, a):
             return B * P * C * sz(dt) * (2 if gA else 1)
         dt, B, P, C = a[12:16]
         return B * P * C * sz(dt) * (3 if gA else 2)
+    if name == "eat_se_bn_bwd_reduce":      # (dp, z, scale, shift, mean, act, dgate, part, parts, dtype, B, P, C): dp + z read, 4 partial sums written
+        parts, dt, B, P, C = a[8:13]
+        return 2 * B * P * C * sz(dt) + parts * 4 * B * C * 4
+    if name == "eat_se_bn_bwd_combine":     # (part, parts, gate, dpool, invstd, B, C, s1, s2)
+        parts, B, C = a[1], a[5], a[6]
+        return (parts * 4 + 2) * B * C * 4
+    if name == "eat_se_bwd_reduce":         # (dp, z, scale, shift, act, dgate, dtype, B, P, C)
+        dt, B, P, C = a[6:10]
+        return 2 * B * P * C * sz(dt)
+    if name == "eat_bn_act_pool":           # (z, scale, shift, act, pool, mul, dtype, B, P, C)
+        dt, B, P, C = a[6:10]
+        return B * P * C * sz(dt)
+    if name == "eat_dw_conv_dgrad_bnred":   # (dz, wt, res, din, z, ..., dtype, B, F, T, C, k, stride): dz + z read, din written
+        res, dt, B, F, T, C, k, s = a[2], a[12], a[13], a[14], a[15], a[16], a[17], a[18]
+        Fo, To = (F + 2 * ((k - 1) // 2) - k) // s + 1, (T + 2 * ((k - 1) // 2) - k) // s + 1
+        return B * C * sz(dt) * (F * T * (3 if res else 2) + Fo * To)
     if name == "eat_dw_conv_dgrad":
         dz, wt, wbs, res, din, dt, B, F, T, C, k, s = a[:12]
         Fo, To = (F + 2 * ((k - 1) // 2) - k) // s + 1, (T + 2 * ((k - 1) // 2) - k) // s + 1
@@ -384,7 +400,11 @@ class KernelTimer:
             e0.record()
             fn(*args)
             e1.record()
-            self.records.append((name, e0, e1, algo_bytes(name, args), args if name in ("eat_pw_tma_fwd", "eat_pw_tc_fwd", "eat_pw_tc_wgrad") else None))
+            try:
+                nbytes = algo_bytes(name, args)
+            except Exception:                     # an accounting slip must never take the measurement down
+                nbytes = None
+            self.records.append((name, e0, e1, nbytes, args if name in ("eat_pw_tma_fwd", "eat_pw_tc_fwd", "eat_pw_tc_wgrad") else None))
         return call
 
     def __exit__(self, *a):
