@@ -185,7 +185,7 @@ def golden_script():
 def golden_script_f4():
     """SURVEY section 8 row f4 (ensemble + windowed inference), reference modules on CPU, fp32:
       * `inference.py --ensemble mn04_as mn10_as` on the wav fixture, unchanged (models/ensemble.py: mean of the logits);
-        (an ensemble with a DyMN member is pinned at the synthetic golden inputs instead, tests/test_gpu_f4.py: on this
+        (an ensemble with a DyMN member is pinned at the synthetic golden inputs instead, tests/test_gpu_zz_f4.py: on this
         recording the synthetic DyMN states overflow -- logits of 1e20 with the reference's own modules -- and pin nothing);
       * `windowed_inference.py` (2 s windows, 1 s hop -> 9 windows of the 10 s fixture): the script's own printout and,
         through tests/golden/windowed_driver.py, EATagger's full-precision result for mn10_as and for the mn04 + mn10 ensemble.
