@@ -81,3 +81,35 @@ def test_depthwise_launch_plan_host_logic():
                             assert rounds * slots <= 1.34 * units, (kind, dtype, (F, T, C, k, s), list(plan), rounds * slots / units)
     with pytest.raises(RuntimeError):
         L.dw_plan(0, 0, 1, 8, 8, 6, 3, 1, 0, ctypes.addressof(plan))       # channels not a multiple of the vector width
+
+
+def test_argument_errors_are_reported_before_any_launch():
+    """Error behaviour of the boundary (int status + message, the shim raises): invalid arguments are
+    rejected on the host, so these calls are safe without a GPU.  Covers the entry points added for the BatchNorm-backward
+    fusions; the binding turns a non-zero status into EatError carrying eat_last_error()."""
+    import pytest
+    from efficientat_b200._lib import EatError, lib
+    L = lib()
+    fake = 4096                                                   # never dereferenced: validation comes first
+    with pytest.raises(EatError, match="multiple of the vector width"):
+        L.se_bn_bwd_reduce(fake, fake, fake, fake, fake, 1, fake, fake, 3, 0, 2, 16, 10, 0)           # C = 10, fp32 vectors of 4
+    with pytest.raises(EatError, match="multiple of the vector width"):
+        L.se_bn_bwd_reduce(fake, fake, fake, fake, fake, 1, fake, fake, 3, 1, 2, 16, 12, 0)           # C = 12, bf16 vectors of 8
+    with pytest.raises(EatError, match="parts and P must be positive"):
+        L.se_bn_bwd_reduce(fake, fake, fake, fake, fake, 1, fake, fake, 0, 0, 2, 16, 16, 0)
+    with pytest.raises(EatError, match="parts must be positive"):
+        L.se_bn_bwd_combine(fake, 0, fake, fake, fake, 2, 16, fake, fake, 0)
+    with pytest.raises(EatError, match="are required"):
+        L.dw_conv_dgrad_bnred(fake, fake, 0, fake, 0, fake, fake, fake, fake, 1, fake, fake, 0, 2, 8, 8, 16, 3, 2, 0)   # z missing
+    with pytest.raises(EatError, match="stride 2"):
+        L.dw_conv_dgrad_bnred(fake, fake, 0, fake, fake, fake, fake, fake, fake, 1, fake, fake, 0, 2, 8, 8, 16, 3, 1, 0)
+    with pytest.raises(EatError, match="fp32 storage"):
+        L.dw_conv_dgrad_bnred(fake, fake, 0, fake, fake, fake, fake, fake, fake, 1, fake, fake, 1, 2, 8, 8, 16, 3, 2, 0)
+    with pytest.raises(EatError, match="multiple of the vector width"):
+        L.bn_bwd_apply(fake, 0, 0, fake, fake, fake, fake, fake, 1, fake, fake, fake, 0, 2, 16, 10, 0)
+    with pytest.raises(EatError, match="multiple of the vector width"):
+        L.bn_act_pool(fake, fake, fake, 1, fake, 1.0, 0, 2, 16, 10, 0)
+    # empty batches are a no-op, not an error
+    L.se_bn_bwd_reduce(fake, fake, fake, fake, fake, 1, fake, fake, 3, 0, 0, 16, 16, 0)
+    L.se_bn_bwd_combine(fake, 3, fake, fake, fake, 0, 16, fake, fake, 0)
+    L.dw_conv_dgrad_bnred(fake, fake, 0, fake, fake, fake, fake, fake, fake, 1, fake, fake, 0, 0, 8, 8, 16, 3, 2, 0)
